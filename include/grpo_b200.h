@@ -1,0 +1,154 @@
+/* grpo_b200.h - C ABI of the B200-native GRPO policy-loss path.
+ *
+ * Every entry point replaces a piece of the reference's (hunarbatra/SpatialThinker, an EasyR1/veRL fork) Python hot
+ * path; the reference has no FFI of its own (it is pure PyTorch), so the "binding" a maintainer adds is the ctypes
+ * stub in INTEGRATION.md / spatialthinker_b200/_lib.py.  Cited lines are relative to the reference checkout.
+ *
+ * Conventions
+ *   - all tensor arguments are DEVICE pointers (row-major, contiguous); the caller owns every buffer, the library
+ *     never allocates or frees device memory and keeps no pointer after returning;
+ *   - every call only ENQUEUES work on `stream` (no host synchronisation, no internal streams);
+ *   - return value: 0 on success, a positive cudaError_t on a CUDA failure, a negative GRPO_ERR_* on bad arguments;
+ *     grpo_last_error() returns a thread-local description; nothing throws across the ABI;
+ *   - `mask_dtype`: 0 = float32, 1 = int64 (the reference's attention_mask slice), 2 = uint8/bool, 3 = no mask (all 1);
+ *   - log-probabilities are log p (negative numbers) - the flash-attn branch of the reference, torch_functional.py:42.
+ */
+#ifndef GRPO_B200_H
+#define GRPO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* grpo_stream_t;
+
+#define GRPO_ERR_ARG (-1)       /* shape / alignment / null-pointer violation */
+#define GRPO_ERR_WORKSPACE (-2) /* workspace too small */
+#define GRPO_ERR_DRIVER (-3)    /* TMA descriptor / driver entry point failure */
+
+/* KL estimator selector - verl/trainer/core_algos.py:394-436 compute_kl(kl_penalty: str) */
+#define GRPO_KL_NONE (-1)
+#define GRPO_KL_LOW_VAR 0 /* "low_var_kl" (shipped default, scripts/config.yaml:22) */
+#define GRPO_KL_KL 1      /* "kl"   */
+#define GRPO_KL_ABS 2     /* "abs"  */
+#define GRPO_KL_MSE 3     /* "mse"  */
+#define GRPO_KL_CHI2 4    /* "chi2" */
+
+/* metric slots written by the loss entry points (float[GRPO_NUM_METRICS], device memory) -
+ * the actor/* keys of verl/workers/actor/dp_actor.py:274-286 */
+#define GRPO_MET_PG_LOSS 0     /* masked_mean(policy loss), before the KL term   core_algos.py:349 */
+#define GRPO_MET_CLIPFRAC_HI 1 /* actor/pg_clipfrac_higher                        core_algos.py:350 */
+#define GRPO_MET_CLIPFRAC_LO 2 /* actor/pg_clipfrac_lower                         core_algos.py:351 */
+#define GRPO_MET_PPO_KL 3      /* actor/ppo_kl                                    core_algos.py:352 */
+#define GRPO_MET_KL_LOSS 4     /* actor/kl_loss                                   dp_actor.py:270   */
+#define GRPO_MET_ENTROPY 5     /* actor/entropy_loss = -masked_mean(log_probs)    dp_actor.py:253   */
+#define GRPO_MET_TOTAL 6       /* actor/pg_loss as logged: pg + kl_coef * kl      dp_actor.py:271   */
+#define GRPO_MET_SCALED 7      /* total / grad_accum, the back-propagated scalar  dp_actor.py:277   */
+#define GRPO_MET_TRUE_ENTROPY 8 /* masked_mean(lse - sum p z) when entropy was requested, else 0      */
+#define GRPO_MET_MASK_SUM 9     /* sum(mask): valid tokens of the micro-batch                        */
+#define GRPO_NUM_METRICS 10
+
+int grpo_abi_version(void);
+const char* grpo_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * lm_head -> token log-prob / entropy, forward only.
+ * Replaces: HF `self.lm_head(hidden_states)` reached from dp_actor.py:118-125, `logits.div_(temperature)` :126 and
+ * `log_probs_from_logits` torch_functional.py:45-66 - without materialising logits.
+ *   hidden  bf16 [rows][hidden_dim]      weight bf16 [vocab][hidden_dim]      labels int64 [rows]
+ *   logp    f32  [rows] (out)            entropy f32 [rows] (out, nullable: lse - sum p z)
+ *   lse     f32  [rows] (out, nullable)
+ * Requires hidden_dim % 64 == 0, vocab % 8 == 0, 16-byte aligned hidden / weight.
+ * ------------------------------------------------------------------------------------------------------------------ */
+size_t grpo_lmhead_fwd_workspace_bytes(int64_t rows, int64_t hidden_dim, int64_t vocab);
+int grpo_lmhead_logprob_fwd(const void* hidden, const void* weight, const int64_t* labels, int64_t rows,
+                            int64_t hidden_dim, int64_t vocab, float temperature, float* logp, float* entropy,
+                            float* lse, void* workspace, size_t workspace_bytes, grpo_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * lm_head backward for arbitrary upstream gradients (the autograd of the call above).
+ * Replaces: flash-attn CE backward + div_ backward + the two lm_head backward GEMMs triggered by `loss.backward()`
+ * dp_actor.py:278.  Recomputes the logits tiles chunk by chunk, never holding more than one chunk's exp-stash.
+ *   dlogp    f32 [rows]  dL/dlogp                       dentropy f32 [rows] dL/dentropy (nullable)
+ *   dhidden  bf16 [rows][hidden_dim] (out, overwritten) dweight  f32 [vocab][hidden_dim] (ACCUMULATED into)
+ * ------------------------------------------------------------------------------------------------------------------ */
+size_t grpo_lmhead_bwd_workspace_bytes(int64_t rows, int64_t hidden_dim, int64_t vocab);
+int grpo_lmhead_bwd(const void* hidden, const void* weight, const int64_t* labels, const float* dlogp,
+                    const float* dentropy, int64_t rows, int64_t hidden_dim, int64_t vocab, float temperature,
+                    void* dhidden, float* dweight, void* workspace, size_t workspace_bytes, grpo_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Fused GRPO loss for ONE micro-batch: lm_head -> log-prob -> ratio / clip / dual-clip / KL / masked means ->
+ * dL/dlogp -> dHidden, dW, in one pass (3 GEMM units, no recompute).
+ * Replaces the body of the micro-batch loop, dp_actor.py:247-278 (+ compute_policy_loss core_algos.py:291-353,
+ * compute_kl :394-436, masked_mean torch_functional.py:69-71).
+ *   rows = micro_batch * response_length; old_logp / advantages / ref_logp (nullable) / mask are [rows]
+ *   loss = (pg_loss + kl_coef * kl_loss - entropy_coef * masked_mean(entropy)) / grad_accum
+ *   logp_out f32 [rows] (out)    entropy_out f32 [rows] (out, nullable unless entropy_coef != 0)
+ *   dhidden bf16 [rows][hidden_dim] (out; nullable together with dweight => forward + metrics only)
+ *   dweight f32 [vocab][hidden_dim] (ACCUMULATED into)       metrics f32 [GRPO_NUM_METRICS] (out)
+ * ------------------------------------------------------------------------------------------------------------------ */
+size_t grpo_fused_loss_workspace_bytes(int64_t rows, int64_t hidden_dim, int64_t vocab);
+int grpo_fused_loss_fwd_bwd(const void* hidden, const void* weight, const int64_t* labels, const float* old_logp,
+                            const float* advantages, const float* ref_logp, const void* mask, int mask_dtype,
+                            int64_t rows, int64_t hidden_dim, int64_t vocab, float temperature, float clip_ratio_low,
+                            float clip_ratio_high, float clip_ratio_dual, int kl_mode, float kl_coef,
+                            float entropy_coef, float grad_accum, float* logp_out, float* entropy_out, void* dhidden,
+                            float* dweight, float* metrics, void* workspace, size_t workspace_bytes,
+                            grpo_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Token-level policy loss on given log-probs (no lm_head): the four masked means of compute_policy_loss
+ * (core_algos.py:291-353), optionally the KL term (compute_kl :394-436) and dL/dlogp with
+ * L = (pg + kl_coef * kl) / grad_accum.   acc_scratch: 8 doubles of device scratch.
+ * ------------------------------------------------------------------------------------------------------------------ */
+int grpo_policy_loss_fwd_bwd(const float* logp, const float* old_logp, const float* advantages, const float* ref_logp,
+                             const void* mask, int mask_dtype, int64_t n, float clip_ratio_low, float clip_ratio_high,
+                             float clip_ratio_dual, int kl_mode, float kl_coef, float grad_accum, float* dlogp,
+                             float* metrics, double* acc_scratch, grpo_stream_t stream);
+
+/* compute_kl (core_algos.py:394-436): out[i] = kl(logp[i], ref[i]); dout_dlogp nullable (d out / d logp). */
+int grpo_compute_kl(const float* logp, const float* ref_logp, int64_t n, int kl_mode, float* out, float* dout_dlogp,
+                    grpo_stream_t stream);
+
+/* masked_mean over all elements (torch_functional.py:69-71): out[0] = sum(x*mask) / (sum(mask) + eps).
+ * acc_scratch: 2 doubles of device scratch. */
+int grpo_masked_mean(const float* x, const void* mask, int mask_dtype, int64_t n, float eps, float* out,
+                     double* acc_scratch, grpo_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * compute_grpo_outcome_advantage (core_algos.py:137-175; caller ray_trainer.py:148-175).
+ *   rewards f32 [bsz][t_len]; mask [bsz][t_len]; order int32 [bsz] = row ids sorted by group;
+ *   offsets int32 [n_groups+1] = group boundaries in `order` (the host maps uid strings to this CSR view);
+ *   advantages f32 [bsz][t_len] (out); seq_scratch f32 [2*bsz] device scratch (scores, normalised scores).
+ * ------------------------------------------------------------------------------------------------------------------ */
+int grpo_advantage(const float* rewards, const void* mask, int mask_dtype, const int32_t* order,
+                   const int32_t* offsets, int64_t bsz, int64_t t_len, int64_t n_groups, float eps, float* advantages,
+                   float* seq_scratch, grpo_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * log_probs_from_logits on MATERIALISED logits (torch_functional.py:45-66), API parity only.
+ *   logits_dtype: 0 = f32, 1 = bf16, 2 = f16;  logits [rows][ld];  logp / entropy / lse f32 [rows] (each nullable)
+ * Backward: dlogits = dlogp * (onehot - softmax) - dentropy * p * (log p + H)   (dlogits may alias logits).
+ * ------------------------------------------------------------------------------------------------------------------ */
+int grpo_logprob_from_logits(const void* logits, int logits_dtype, const int64_t* labels, int64_t rows, int64_t vocab,
+                             int64_t ld, float* logp, float* entropy, float* lse, grpo_stream_t stream);
+int grpo_logprob_from_logits_bwd(const void* logits, int logits_dtype, const int64_t* labels, const float* lse,
+                                 const float* dlogp, const float* dentropy, const float* entropy, int64_t rows,
+                                 int64_t vocab, int64_t ld, void* dlogits, int64_t ld_out, grpo_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Debug / test entry: plain tcgen05 GEMM  C[m][n] (f32) = A . B^T-style product with selectable operand majorness.
+ *   a_mn_major == 0: A is [m][k] row-major, else A is [k][m] row-major; same for B with n.
+ *   cta_group: 1 or 2.   accumulate != 0: C += (red.global.add).
+ * ------------------------------------------------------------------------------------------------------------------ */
+int grpo_debug_gemm(const void* a, const void* b, float* c, int64_t m, int64_t n, int64_t k, int a_mn_major,
+                    int b_mn_major, int cta_group, int accumulate, grpo_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRPO_B200_H */

@@ -1,0 +1,294 @@
+// Persistent, warp-specialised tcgen05 GEMM main loop for sm_100a (bf16 x bf16 -> fp32 in TMEM).
+//
+//   warp 0      : TMA producer (one lane) - cp.async.bulk.tensor into a kStages-deep smem ring
+//   warp 1      : MMA issuer (one lane, pair leader only) - tcgen05.mma, accumulators double-buffered in TMEM
+//   warp 2      : TMEM allocator
+//   warps 4..7  : epilogue - tcgen05.ld; thread i of the warpgroup owns accumulator row i (TMEM lane i)
+//
+// kCta == 2 runs one 256 x BLOCK_N tile on a CTA pair (cta_group::2): each CTA loads its own 128 rows of A and half
+// of the B tile, the leader issues the MMAs for both, each CTA drains its own 128 accumulator rows.
+//
+// Operand majorness is a template parameter: K-major operands are [rows][K] row-major in global memory, MN-major
+// operands are [K][rows] row-major (the "transposed" reads the backward GEMMs need) - both are fed by plain 2-D TMA
+// boxes in 128-byte-swizzle layout, so no transposed copies are ever materialised in HBM.
+#pragma once
+#include "ptx.cuh"
+
+namespace grpo {
+
+constexpr int kBlockM = 128;  // accumulator rows per CTA (= TMEM lanes)
+constexpr int kBlockK = 64;   // 64 bf16 = one 128-byte swizzle row
+constexpr int kUmmaK = 16;
+constexpr int kNumThreads = 256;
+constexpr int kEpiWarp0 = 4;
+constexpr int kNumEpiThreads = 128;
+
+// Tile walk: tiles are grouped in panels of `panel_m` row-blocks; inside a panel either the row-block index (m_fast)
+// or the column-block index runs fastest. Chosen per GEMM so that the operand re-read by neighbouring CTAs is the
+// one that stays resident in L2.
+struct TileSched {
+  uint32_t m_blocks;  // row blocks of 128*kCta
+  uint32_t n_blocks;  // column blocks of BLOCK_N
+  uint32_t k_blocks;  // K blocks of 64
+  uint32_t panel_m;   // row blocks per panel
+  uint32_t m_fast;
+};
+
+__device__ __forceinline__ void decode_tile(const TileSched& s, uint32_t t, uint32_t& m_blk, uint32_t& n_blk) {
+  const uint32_t per_panel = s.panel_m * s.n_blocks;
+  const uint32_t p = t / per_panel;
+  const uint32_t r = t - p * per_panel;
+  const uint32_t m0 = p * s.panel_m;
+  const uint32_t pm = min(s.panel_m, s.m_blocks - m0);
+  if (s.m_fast) {
+    n_blk = r / pm;
+    m_blk = m0 + (r - n_blk * pm);
+  } else {
+    const uint32_t mm = r / s.n_blocks;
+    m_blk = m0 + mm;
+    n_blk = r - mm * s.n_blocks;
+  }
+}
+
+// What an epilogue sees for one accumulator tile.
+struct EpiCtx {
+  uint32_t m_blk, n_blk;
+  uint32_t row_in_tile;  // 0 .. 128*kCta-1 : this thread's accumulator row inside the (pair) tile
+  uint32_t warp, lane;   // epilogue warp 0..3, lane
+  uint32_t tmem_acc;     // TMEM address of this warp's lanes, column 0 of the accumulator stage
+};
+
+template <int kCta, int BLOCK_N, int kStages, bool kAMn, bool kBMn>
+struct GemmCfg {
+  static constexpr int kLoadN = BLOCK_N / kCta;  // B columns each CTA loads
+  static constexpr int kABytes = kBlockM * kBlockK * 2;
+  static constexpr int kBBytes = kLoadN * kBlockK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kRingBytes = kStages * kStageBytes;
+  static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
+  static constexpr int kTmemCols = 2 * BLOCK_N;
+  static_assert(kTmemCols == 512 || kTmemCols == 256 || kTmemCols == 128 || kTmemCols == 64, "TMEM columns");
+  static_assert(BLOCK_N % 16 == 0 && BLOCK_N <= 256, "UMMA N");
+  static constexpr size_t smem_bytes(int epi_bytes) { return 1024 + kRingBytes + epi_bytes + kBarBytes; }
+};
+
+template <int kCta, int BLOCK_N, int kStages, bool kAMn, bool kBMn, class Epi>
+__global__ void __launch_bounds__(kNumThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+            const TileSched sched, const typename Epi::Params ep) {
+  using Cfg = GemmCfg<kCta, BLOCK_N, kStages, kAMn, kBMn>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * Cfg::kABytes;
+  uint8_t* smem_epi = smem + Cfg::kRingBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kRingBytes + Epi::kSmemBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kStages;
+  uint64_t* tmem_full = bars + 2 * kStages;
+  uint64_t* tmem_empty = bars + 2 * kStages + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t rank = (kCta == 2) ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], kCta);  // one arrive per CTA producer (+ transaction bytes), on the leader
+      mbar_init(&empty_bar[i], 1);    // one tcgen05.commit (multicast to both CTAs)
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);                        // one tcgen05.commit
+      mbar_init(&tmem_empty[i], kCta * kNumEpiThreads);  // every epilogue thread of the pair, on the leader
+    }
+    fence_mbar_init();
+  }
+  __syncwarp();
+  if (kCta == 2) cluster_sync_all();  // peer must be resident before a pair-wide TMEM allocation
+  if (warp == 2) tmem_alloc<kCta>(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  if (kCta == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const uint32_t num_tiles = sched.m_blocks * sched.n_blocks;
+  const uint32_t first_tile = blockIdx.x / kCta;
+  const uint32_t tile_step = gridDim.x / kCta;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (uint32_t t = first_tile; t < num_tiles; t += tile_step) {
+        uint32_t m_blk, n_blk;
+        decode_tile(sched, t, m_blk, n_blk);
+        const int32_t m0 = static_cast<int32_t>(m_blk * (kBlockM * kCta) + rank * kBlockM);
+        const int32_t n0 = static_cast<int32_t>(n_blk * BLOCK_N + rank * Cfg::kLoadN);
+        for (uint32_t kb = 0; kb < sched.k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          const int32_t k0 = static_cast<int32_t>(kb * kBlockK);
+          uint8_t* sa = smem_a + stage * Cfg::kABytes;
+          uint8_t* sb = smem_b + stage * Cfg::kBBytes;
+          if constexpr (!kAMn) {
+            tma_load_2d<kCta>(&tmap_a, &full_bar[stage], sa, k0, m0);
+          } else {
+#pragma unroll
+            for (int i = 0; i < kBlockM / 64; ++i)
+              tma_load_2d<kCta>(&tmap_a, &full_bar[stage], sa + i * (kBlockK * 128), m0 + i * 64, k0);
+          }
+          if constexpr (!kBMn) {
+            tma_load_2d<kCta>(&tmap_b, &full_bar[stage], sb, k0, n0);
+          } else {
+#pragma unroll
+            for (int i = 0; i < Cfg::kLoadN / 64; ++i)
+              tma_load_2d<kCta>(&tmap_b, &full_bar[stage], sb + i * (kBlockK * 128), n0 + i * 64, k0);
+          }
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes * kCta);
+          else mbar_arrive_cluster(&full_bar[stage], 0);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (pair leader only)
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kBlockM * kCta, BLOCK_N, kAMn, kBMn);
+      constexpr uint32_t a_lbo = kAMn ? kBlockK * 128 : 0, b_lbo = kBMn ? kBlockK * 128 : 0;
+      constexpr uint32_t a_kstep = kAMn ? kUmmaK * 128 : kUmmaK * 2, b_kstep = kBMn ? kUmmaK * 128 : kUmmaK * 2;
+      uint32_t stage = 0, phase = 0, it = 0;
+      for (uint32_t t = first_tile; t < num_tiles; t += tile_step, ++it) {
+        const uint32_t as = it & 1, ap = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[as], ap ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+        for (uint32_t kb = 0; kb < sched.k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem_a + stage * Cfg::kABytes);
+          const uint32_t b_addr = smem_u32(smem_b + stage * Cfg::kBBytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            const uint64_t da = make_smem_desc(a_addr + k * a_kstep, 1024, a_lbo);
+            const uint64_t db = make_smem_desc(b_addr + k * b_kstep, 1024, b_lbo);
+            umma_bf16<kCta>(d_tmem, da, db, idesc, (kb | k) != 0);
+          }
+          umma_commit<kCta>(&empty_bar[stage]);  // frees the smem slot (both CTAs) when these MMAs retire
+          if (kb + 1 == sched.k_blocks) umma_commit<kCta>(&tmem_full[as]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+      // the peer's last remote arrivals must land before this CTA's barriers go away
+      if (kCta == 2 && it > 0) {
+        const uint32_t last = it - 1;
+        mbar_wait(&tmem_empty[last & 1], (last >> 1) & 1);
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ------------------------------------------------------------------ epilogue
+    const uint32_t ew = warp - kEpiWarp0;
+    uint32_t it = 0;
+    for (uint32_t t = first_tile; t < num_tiles; t += tile_step, ++it) {
+      const uint32_t as = it & 1, ap = (it >> 1) & 1;
+      EpiCtx c;
+      decode_tile(sched, t, c.m_blk, c.n_blk);
+      c.warp = ew;
+      c.lane = lane;
+      c.row_in_tile = rank * kBlockM + ew * 32 + lane;
+      c.tmem_acc = tmem_base + as * BLOCK_N + ((ew * 32u) << 16);
+      mbar_wait(&tmem_full[as], ap);
+      tc_fence_after();
+      Epi::run(ep, c, smem_epi);  // returns with all of its TMEM loads complete
+      tc_fence_before();
+      if (leader) mbar_arrive(&tmem_empty[as]);
+      else mbar_arrive_cluster(&tmem_empty[as], 0);
+    }
+  }
+
+  __syncwarp();  // re-converge the single-lane roles before the aligned barriers below
+  tc_fence_before();
+  if (kCta == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 2) tmem_dealloc<kCta>(tmem_base, Cfg::kTmemCols);
+}
+
+// ------------------------------------------------------------------------------------------
+// Generic epilogues
+// ------------------------------------------------------------------------------------------
+// fp32 result, plain store or accumulate (red.global.add) into C[M][ldc].
+template <int kCta, int BLOCK_N>
+struct EpiF32 {
+  struct Params {
+    float* c;
+    int64_t ldc;
+    uint32_t m, n;
+    uint32_t accumulate;
+  };
+  static constexpr int kSmemBytes = 0;
+  __device__ static void run(const Params& p, const EpiCtx& c, uint8_t*) {
+    const uint32_t row = c.m_blk * (kBlockM * kCta) + c.row_in_tile;
+    const uint32_t col0 = c.n_blk * BLOCK_N;
+    float* out = p.c + static_cast<int64_t>(row) * p.ldc + col0;
+#pragma unroll 1
+    for (int g = 0; g < BLOCK_N / 32; ++g) {
+      uint32_t v[32];
+      tmem_ld_32x32(c.tmem_acc + g * 32, v);
+      tmem_ld_wait();
+      if (row < p.m) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const uint32_t col = col0 + g * 32 + q * 4;
+          if (col < p.n) {  // n % 4 == 0
+            float4 f = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                                   __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+            float4* dst = reinterpret_cast<float4*>(out + g * 32 + q * 4);
+            if (p.accumulate) atomicAdd(dst, f);
+            else *dst = f;
+          }
+        }
+      }
+    }
+  }
+};
+
+// bf16 result, plain store into C[M][ldc].
+template <int kCta, int BLOCK_N>
+struct EpiBF16 {
+  struct Params {
+    __nv_bfloat16* c;
+    int64_t ldc;
+    uint32_t m, n;
+  };
+  static constexpr int kSmemBytes = 0;
+  __device__ static void run(const Params& p, const EpiCtx& c, uint8_t*) {
+    const uint32_t row = c.m_blk * (kBlockM * kCta) + c.row_in_tile;
+    const uint32_t col0 = c.n_blk * BLOCK_N;
+    __nv_bfloat16* out = p.c + static_cast<int64_t>(row) * p.ldc + col0;
+#pragma unroll 1
+    for (int g = 0; g < BLOCK_N / 32; ++g) {
+      uint32_t v[32];
+      tmem_ld_32x32(c.tmem_acc + g * 32, v);
+      tmem_ld_wait();
+      if (row < p.m) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t col = col0 + g * 32 + q * 8;
+          if (col < p.n) {  // n % 8 == 0
+            uint4 pk;
+            pk.x = pack_bf16x2(__uint_as_float(v[8 * q + 0]), __uint_as_float(v[8 * q + 1]));
+            pk.y = pack_bf16x2(__uint_as_float(v[8 * q + 2]), __uint_as_float(v[8 * q + 3]));
+            pk.z = pack_bf16x2(__uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5]));
+            pk.w = pack_bf16x2(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7]));
+            *reinterpret_cast<uint4*>(out + g * 32 + q * 8) = pk;
+          }
+        }
+      }
+    }
+  }
+};
+
+}  // namespace grpo

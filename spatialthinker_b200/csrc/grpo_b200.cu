@@ -1,0 +1,577 @@
+// C ABI (include/grpo_b200.h) over the sm_100a kernels. Host side only: argument checks, TMA descriptors,
+// workspace carving, launch sequencing on the caller's stream. No allocation, no synchronisation.
+#include "../../include/grpo_b200.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+#include "advantage_kernels.cuh"
+#include "gemm_core.cuh"
+#include "lmhead_kernels.cuh"
+#include "logits_kernels.cuh"
+#include "loss_kernels.cuh"
+
+namespace grpo {
+
+// ------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define GRPO_CUDA(expr)                                                                         \
+  do {                                                                                          \
+    cudaError_t e__ = (expr);                                                                   \
+    if (e__ != cudaSuccess) return fail(static_cast<int>(e__), "%s: %s", #expr, cudaGetErrorString(e__)); \
+  } while (0)
+#define GRPO_TRY(expr)        \
+  do {                        \
+    int rc__ = (expr);        \
+    if (rc__ != 0) return rc__; \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------ TMA descriptors
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// 2-D bf16 tensor [outer][inner] (inner contiguous, row pitch `pitch_elems`), box = [box_outer][box_inner],
+// 128-byte swizzle, out-of-bounds reads return zeros.
+static int make_tmap_bf16(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_elems,
+                          uint32_t box_inner, uint32_t box_outer) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(GRPO_ERR_DRIVER, "cuTensorMapEncodeTiled entry point not available");
+  if ((reinterpret_cast<uintptr_t>(base) & 15u) || (pitch_elems * 2) % 16 != 0)
+    return fail(GRPO_ERR_ARG, "TMA operand must be 16-byte aligned with a 16-byte multiple row pitch");
+  const cuuint64_t dims[2] = {inner, outer};
+  const cuuint64_t strides[1] = {pitch_elems * 2};
+  const cuuint32_t box[2] = {box_inner, box_outer};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(GRPO_ERR_DRIVER, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return 0;
+}
+
+// operand [rows][k] (K-major) or [k][rows] (MN-major) -> descriptor with the box the producer warp expects
+static int make_operand_tmap(CUtensorMap* map, const void* base, uint64_t rows, uint64_t k, uint64_t pitch_elems,
+                             bool mn_major, uint32_t rows_per_load) {
+  if (!mn_major) return make_tmap_bf16(map, base, k, rows, pitch_elems, kBlockK, rows_per_load);
+  return make_tmap_bf16(map, base, rows, k, pitch_elems, 64, kBlockK);
+}
+
+// ------------------------------------------------------------------------------------------ device info
+struct DevInfo {
+  int sms = 0;
+  int cta_group = 2;
+};
+static int get_dev(DevInfo* out) {
+  static DevInfo cached[64];
+  static bool have[64] = {};
+  int dev = 0;
+  GRPO_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return fail(GRPO_ERR_ARG, "device ordinal out of range");
+  if (!have[dev]) {
+    cudaDeviceProp p;
+    GRPO_CUDA(cudaGetDeviceProperties(&p, dev));
+    if (p.major != 10) return fail(GRPO_ERR_ARG, "this library targets sm_100a (B200); found sm_%d%d", p.major, p.minor);
+    cached[dev].sms = p.multiProcessorCount;
+    const char* e = getenv("GRPO_CTA_GROUP");
+    cached[dev].cta_group = (e && e[0] == '1') ? 1 : 2;
+    have[dev] = true;
+  }
+  *out = cached[dev];
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ GEMM launch
+template <int kCta, int BLOCK_N, int kStages, bool kAMn, bool kBMn, class Epi>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const TileSched& sched,
+                       const typename Epi::Params& ep, int sms, cudaStream_t stream) {
+  using Cfg = GemmCfg<kCta, BLOCK_N, kStages, kAMn, kBMn>;
+  auto kern = gemm_kernel<kCta, BLOCK_N, kStages, kAMn, kBMn, Epi>;
+  const size_t smem = Cfg::smem_bytes(Epi::kSmemBytes);
+  GRPO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  const uint32_t tiles = sched.m_blocks * sched.n_blocks;
+  if (tiles == 0) return 0;
+  uint32_t groups = static_cast<uint32_t>(sms / kCta);
+  if (groups > tiles) groups = tiles;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(groups * kCta);
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCta;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  GRPO_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, sched, ep));
+  return 0;
+}
+
+constexpr int kBlockN = 256;
+constexpr int kStages1 = 4;  // 48 KB / stage
+constexpr int kStages2 = 6;  // 32 KB / stage (each CTA of the pair loads half of B)
+
+static inline uint32_t cdiv(uint64_t a, uint64_t b) { return static_cast<uint32_t>((a + b - 1) / b); }
+
+// Rows per chunk of the chunked lm_head pipeline: 37 row-blocks of 256. With 74 CTA pairs, 37 x (H/256) output tiles
+// of the dHidden GEMM is a whole number of waves for H = 2048 (4) and H = 3584 (7); the chunk's exp-stash is
+// 9472 x V bf16 (2.9 GB at V = 151936).
+constexpr int64_t kChunkRows = 9472;
+
+template <bool kAMn, bool kBMn, class Epi1, class Epi2>
+static int launch_gemm_any(int cta_group, const void* a, uint64_t a_rows, uint64_t a_pitch, const void* b,
+                           uint64_t b_rows, uint64_t b_pitch, uint64_t k, TileSched sched,
+                           const typename Epi1::Params& ep1, const typename Epi2::Params& ep2, int sms,
+                           cudaStream_t stream) {
+  CUtensorMap ta, tb;
+  GRPO_TRY(make_operand_tmap(&ta, a, a_rows, k, a_pitch, kAMn, kBlockM));
+  GRPO_TRY(make_operand_tmap(&tb, b, b_rows, k, b_pitch, kBMn, kBlockN / cta_group));
+  sched.m_blocks = cdiv(a_rows, kBlockM * cta_group);
+  sched.n_blocks = cdiv(b_rows, kBlockN);
+  sched.k_blocks = cdiv(k, kBlockK);
+  if (sched.panel_m == 0 || sched.panel_m > sched.m_blocks) sched.panel_m = sched.m_blocks;
+  if (cta_group == 1) return launch_gemm<1, kBlockN, kStages1, kAMn, kBMn, Epi1>(ta, tb, sched, ep1, sms, stream);
+  return launch_gemm<2, kBlockN, kStages2, kAMn, kBMn, Epi2>(ta, tb, sched, ep2, sms, stream);
+}
+
+// ------------------------------------------------------------------------------------------ workspace
+struct Workspace {
+  // sizes for one chunk
+  int64_t chunk_rows = 0, rows_pad = 0, n_tiles = 0;
+  __nv_bfloat16* stash = nullptr;
+  float *part_max = nullptr, *part_sum = nullptr, *part_ez = nullptr;
+  float *target_z = nullptr, *lse = nullptr, *dlogp = nullptr, *dent = nullptr, *ent = nullptr;
+  double* acc = nullptr;
+  size_t bytes = 0;
+};
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static Workspace carve(void* base, int64_t rows, int64_t vocab, bool with_stash) {
+  Workspace w;
+  w.chunk_rows = rows < kChunkRows ? rows : kChunkRows;
+  if (w.chunk_rows < 1) w.chunk_rows = 1;
+  w.rows_pad = static_cast<int64_t>(align_up(static_cast<size_t>(w.chunk_rows), 256));
+  w.n_tiles = (vocab + kBlockN - 1) / kBlockN;
+  size_t off = 0;
+  uint8_t* p = static_cast<uint8_t*>(base);
+  auto take = [&](size_t nbytes) {
+    uint8_t* r = p ? p + off : nullptr;
+    off = align_up(off + nbytes, 1024);
+    return r;
+  };
+  if (with_stash) w.stash = reinterpret_cast<__nv_bfloat16*>(take(static_cast<size_t>(w.chunk_rows) * vocab * 2));
+  const size_t part = static_cast<size_t>(w.n_tiles) * w.rows_pad * 4;
+  w.part_max = reinterpret_cast<float*>(take(part));
+  w.part_sum = reinterpret_cast<float*>(take(part));
+  w.part_ez = reinterpret_cast<float*>(take(part));
+  const size_t vec = static_cast<size_t>(w.rows_pad) * 4;
+  w.target_z = reinterpret_cast<float*>(take(vec));
+  w.lse = reinterpret_cast<float*>(take(vec));
+  w.dlogp = reinterpret_cast<float*>(take(vec));
+  w.dent = reinterpret_cast<float*>(take(vec));
+  w.ent = reinterpret_cast<float*>(take(vec));
+  w.acc = reinterpret_cast<double*>(take(ACC_N * sizeof(double)));
+  w.bytes = off;
+  return w;
+}
+
+static int check_head_args(const void* hidden, const void* weight, int64_t rows, int64_t h, int64_t v, float temp) {
+  if (!hidden || !weight) return fail(GRPO_ERR_ARG, "hidden / weight must not be null");
+  if (rows < 0 || h <= 0 || v <= 0) return fail(GRPO_ERR_ARG, "negative or zero dimension");
+  if (h % 64 != 0) return fail(GRPO_ERR_ARG, "hidden_dim must be a multiple of 64 (got %lld)", (long long)h);
+  if (v % 8 != 0) return fail(GRPO_ERR_ARG, "vocab must be a multiple of 8 (got %lld)", (long long)v);
+  if (!(temp > 0.f)) return fail(GRPO_ERR_ARG, "temperature must be positive");
+  if (rows > 0x7fffffffll || v > 0x7fffffffll) return fail(GRPO_ERR_ARG, "dimension exceeds 2^31");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ chunk steps
+// logits GEMM + softmax statistics (+ optional exp stash) + per-row combine for rows [r0, r0 + n)
+static int chunk_forward(const DevInfo& dev, const Workspace& w, const __nv_bfloat16* hidden,
+                         const __nv_bfloat16* weight, const int64_t* labels, int64_t r0, int64_t n, int64_t h,
+                         int64_t v, float temperature, bool want_entropy, bool want_stash, float* logp_out,
+                         float* ent_out, float* lse_out, cudaStream_t stream) {
+  EpiSoftmax<1, kBlockN>::Params p1;
+  p1.rows = static_cast<uint32_t>(n);
+  p1.vocab = static_cast<uint32_t>(v);
+  p1.rows_pad = static_cast<uint32_t>(w.rows_pad);
+  p1.scale = 1.f / temperature;
+  p1.part_max = w.part_max;
+  p1.part_sum = w.part_sum;
+  p1.part_ez = want_entropy ? w.part_ez : nullptr;
+  p1.labels = labels + r0;
+  p1.target_z = w.target_z;
+  p1.stash = want_stash ? w.stash : nullptr;
+  p1.ld_stash = v;
+  EpiSoftmax<2, kBlockN>::Params p2;
+  memcpy(&p2, &p1, sizeof(p1));
+  static_assert(sizeof(p1) == sizeof(p2), "epilogue params layout");
+  GRPO_CUDA(cudaMemsetAsync(w.target_z, 0, static_cast<size_t>(n) * 4, stream));
+  TileSched s{};
+  s.m_fast = 1;  // walk all row blocks of the chunk under one vocab tile: hidden chunk stays in L2, W streams once
+  GRPO_TRY((launch_gemm_any<false, false, EpiSoftmax<1, kBlockN>, EpiSoftmax<2, kBlockN>>(
+      dev.cta_group, hidden + r0 * h, n, h, weight, v, h, h, s, p1, p2, dev.sms, stream)));
+  const uint32_t threads = 128;
+  combine_rows_kernel<<<cdiv(n, threads), threads, 0, stream>>>(
+      w.part_max, w.part_sum, want_entropy ? w.part_ez : nullptr, w.target_z, labels + r0, static_cast<uint32_t>(n),
+      static_cast<uint32_t>(w.rows_pad), static_cast<uint32_t>(w.n_tiles), static_cast<uint32_t>(v), lse_out,
+      logp_out, ent_out);
+  GRPO_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// stash -> dlogits, dHidden = dlogits . W, dW += dlogits^T . hidden for rows [r0, r0 + n)
+static int chunk_backward(const DevInfo& dev, const Workspace& w, const __nv_bfloat16* hidden,
+                          const __nv_bfloat16* weight, const int64_t* labels, const float* dlogp, const float* dent,
+                          const float* ent, const float* lse, int64_t r0, int64_t n, int64_t h, int64_t v,
+                          float temperature, __nv_bfloat16* dhidden, float* dweight, cudaStream_t stream) {
+  {
+    dim3 grid(cdiv(v / 8, 256 * 4), static_cast<uint32_t>(n < 65535 ? n : 65535));
+    stash_to_dlogits_kernel<kBlockN><<<grid, 256, 0, stream>>>(
+        w.stash, v, static_cast<uint32_t>(n), static_cast<uint32_t>(v), w.part_max, static_cast<uint32_t>(w.rows_pad),
+        lse, dlogp, dent, ent, labels + r0, 1.f / temperature);
+    GRPO_CUDA(cudaGetLastError());
+  }
+  {  // dHidden[n][h] = G[n][v] . W[v][h]       A = G (K-major), B = W read "transposed" (MN-major)
+    EpiBF16<1, kBlockN>::Params p1{dhidden + r0 * h, h, static_cast<uint32_t>(n), static_cast<uint32_t>(h)};
+    EpiBF16<2, kBlockN>::Params p2{dhidden + r0 * h, h, static_cast<uint32_t>(n), static_cast<uint32_t>(h)};
+    TileSched s{};
+    s.m_fast = 0;  // all H column blocks of a few row blocks run together: W streams once per wave
+    GRPO_TRY((launch_gemm_any<false, true, EpiBF16<1, kBlockN>, EpiBF16<2, kBlockN>>(
+        dev.cta_group, w.stash, n, v, weight, h, h, v, s, p1, p2, dev.sms, stream)));
+  }
+  {  // dW[v][h] += G^T[v][n] . hidden[n][h]    A = G read transposed (MN-major), B = hidden read transposed
+    EpiF32<1, kBlockN>::Params p1{dweight, h, static_cast<uint32_t>(v), static_cast<uint32_t>(h), 1u};
+    EpiF32<2, kBlockN>::Params p2{dweight, h, static_cast<uint32_t>(v), static_cast<uint32_t>(h), 1u};
+    TileSched s{};
+    s.m_fast = 0;  // the H column blocks of one vocab block run together: the G panel is read from HBM once
+    GRPO_TRY((launch_gemm_any<true, true, EpiF32<1, kBlockN>, EpiF32<2, kBlockN>>(
+        dev.cta_group, w.stash, v, v, hidden + r0 * h, h, h, n, s, p1, p2, dev.sms, stream)));
+  }
+  return 0;
+}
+
+static LossCfg make_loss_cfg(float clip_lo, float clip_hi, float clip_dual, int kl_mode, float kl_coef,
+                             float grad_accum) {
+  LossCfg c;
+  c.log_clip_lo = static_cast<float>(log(1.0 - static_cast<double>(clip_lo)));
+  c.log_clip_hi = static_cast<float>(log(1.0 + static_cast<double>(clip_hi)));
+  c.clip_dual = clip_dual;
+  c.kl_coef = kl_coef;
+  c.kl_mode = kl_mode;
+  c.inv_grad_accum = 1.f / grad_accum;
+  return c;
+}
+static inline uint32_t ew_blocks(int64_t n, int threads, int sms) {
+  const int64_t want = (n + threads - 1) / threads;
+  const int64_t cap = static_cast<int64_t>(sms > 0 ? sms : 148) * 8;
+  return static_cast<uint32_t>(want < 1 ? 1 : (want > cap ? cap : want));
+}
+
+}  // namespace grpo
+
+using namespace grpo;
+
+// ============================================================================================ C ABI
+extern "C" {
+
+int grpo_abi_version(void) { return 1; }
+const char* grpo_last_error(void) { return g_err; }
+
+size_t grpo_lmhead_fwd_workspace_bytes(int64_t rows, int64_t, int64_t vocab) {
+  return carve(nullptr, rows, vocab, false).bytes;
+}
+size_t grpo_lmhead_bwd_workspace_bytes(int64_t rows, int64_t, int64_t vocab) {
+  return carve(nullptr, rows, vocab, true).bytes;
+}
+size_t grpo_fused_loss_workspace_bytes(int64_t rows, int64_t, int64_t vocab) {
+  return carve(nullptr, rows, vocab, true).bytes;
+}
+
+int grpo_lmhead_logprob_fwd(const void* hidden, const void* weight, const int64_t* labels, int64_t rows,
+                            int64_t hidden_dim, int64_t vocab, float temperature, float* logp, float* entropy,
+                            float* lse, void* workspace, size_t workspace_bytes, grpo_stream_t stream) {
+  GRPO_TRY(check_head_args(hidden, weight, rows, hidden_dim, vocab, temperature));
+  if (!labels || !logp) return fail(GRPO_ERR_ARG, "labels / logp must not be null");
+  if (rows == 0) return 0;
+  DevInfo dev;
+  GRPO_TRY(get_dev(&dev));
+  const Workspace w = carve(workspace, rows, vocab, false);
+  if (!workspace || workspace_bytes < w.bytes)
+    return fail(GRPO_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
+  auto* hp = static_cast<const __nv_bfloat16*>(hidden);
+  auto* wp = static_cast<const __nv_bfloat16*>(weight);
+  for (int64_t r0 = 0; r0 < rows; r0 += w.chunk_rows) {
+    const int64_t n = (rows - r0 < w.chunk_rows) ? rows - r0 : w.chunk_rows;
+    GRPO_TRY(chunk_forward(dev, w, hp, wp, labels, r0, n, hidden_dim, vocab, temperature, entropy != nullptr, false,
+                           logp + r0, entropy ? entropy + r0 : nullptr, lse ? lse + r0 : nullptr, stream));
+  }
+  return 0;
+}
+
+int grpo_lmhead_bwd(const void* hidden, const void* weight, const int64_t* labels, const float* dlogp,
+                    const float* dentropy, int64_t rows, int64_t hidden_dim, int64_t vocab, float temperature,
+                    void* dhidden, float* dweight, void* workspace, size_t workspace_bytes, grpo_stream_t stream) {
+  GRPO_TRY(check_head_args(hidden, weight, rows, hidden_dim, vocab, temperature));
+  if (!labels || !dlogp || !dhidden || !dweight)
+    return fail(GRPO_ERR_ARG, "labels / dlogp / dhidden / dweight must not be null");
+  if (rows == 0) return 0;
+  DevInfo dev;
+  GRPO_TRY(get_dev(&dev));
+  const Workspace w = carve(workspace, rows, vocab, true);
+  if (!workspace || workspace_bytes < w.bytes)
+    return fail(GRPO_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
+  auto* hp = static_cast<const __nv_bfloat16*>(hidden);
+  auto* wp = static_cast<const __nv_bfloat16*>(weight);
+  for (int64_t r0 = 0; r0 < rows; r0 += w.chunk_rows) {
+    const int64_t n = (rows - r0 < w.chunk_rows) ? rows - r0 : w.chunk_rows;
+    GRPO_TRY(chunk_forward(dev, w, hp, wp, labels, r0, n, hidden_dim, vocab, temperature, dentropy != nullptr, true,
+                           nullptr, dentropy ? w.ent : nullptr, w.lse, stream));
+    GRPO_TRY(chunk_backward(dev, w, hp, wp, labels, dlogp + r0, dentropy ? dentropy + r0 : nullptr, w.ent, w.lse, r0,
+                            n, hidden_dim, vocab, temperature, static_cast<__nv_bfloat16*>(dhidden), dweight, stream));
+  }
+  return 0;
+}
+
+int grpo_fused_loss_fwd_bwd(const void* hidden, const void* weight, const int64_t* labels, const float* old_logp,
+                            const float* advantages, const float* ref_logp, const void* mask, int mask_dtype,
+                            int64_t rows, int64_t hidden_dim, int64_t vocab, float temperature, float clip_ratio_low,
+                            float clip_ratio_high, float clip_ratio_dual, int kl_mode, float kl_coef,
+                            float entropy_coef, float grad_accum, float* logp_out, float* entropy_out, void* dhidden,
+                            float* dweight, float* metrics, void* workspace, size_t workspace_bytes,
+                            grpo_stream_t stream) {
+  GRPO_TRY(check_head_args(hidden, weight, rows, hidden_dim, vocab, temperature));
+  if (!labels || !old_logp || !advantages || !logp_out || !metrics)
+    return fail(GRPO_ERR_ARG, "labels / old_logp / advantages / logp_out / metrics must not be null");
+  if ((dhidden == nullptr) != (dweight == nullptr))
+    return fail(GRPO_ERR_ARG, "dhidden and dweight must be given together");
+  if (mask_dtype < 0 || mask_dtype > 3 || (mask_dtype != MASK_NONE && !mask))
+    return fail(GRPO_ERR_ARG, "bad mask / mask_dtype");
+  if (kl_mode < GRPO_KL_NONE || kl_mode > GRPO_KL_CHI2) return fail(GRPO_ERR_ARG, "unknown kl_mode %d", kl_mode);
+  if (kl_mode != GRPO_KL_NONE && !ref_logp) return fail(GRPO_ERR_ARG, "kl_mode set but ref_logp is null");
+  if (entropy_coef != 0.f && !entropy_out) return fail(GRPO_ERR_ARG, "entropy_coef != 0 needs entropy_out");
+  if (!(grad_accum > 0.f)) return fail(GRPO_ERR_ARG, "grad_accum must be positive");
+  DevInfo dev;
+  GRPO_TRY(get_dev(&dev));
+  const bool want_bwd = dhidden != nullptr;
+  const Workspace w = carve(workspace, rows, vocab, true);
+  if (!workspace || workspace_bytes < w.bytes)
+    return fail(GRPO_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
+  LossCfg cfg = make_loss_cfg(clip_ratio_low, clip_ratio_high, clip_ratio_dual, kl_mode, kl_coef, grad_accum);
+  cfg.entropy_coef = entropy_coef;
+  auto* hp = static_cast<const __nv_bfloat16*>(hidden);
+  auto* wp = static_cast<const __nv_bfloat16*>(weight);
+  const size_t esz = (mask_dtype == MASK_F32) ? 4 : (mask_dtype == MASK_I64 ? 8 : 1);
+
+  GRPO_CUDA(cudaMemsetAsync(w.acc, 0, ACC_N * sizeof(double), stream));
+  if (rows > 0) {
+    // the normaliser sum(mask) spans the whole micro-batch and is needed before the first dL/dlogp (dp_actor.py:255)
+    mask_sum_kernel<<<ew_blocks(rows, 256, dev.sms), 256, 0, stream>>>(mask, mask_dtype, static_cast<size_t>(rows),
+                                                                        w.acc);
+    GRPO_CUDA(cudaGetLastError());
+  }
+  const bool want_ent = entropy_out != nullptr;
+  for (int64_t r0 = 0; r0 < rows; r0 += w.chunk_rows) {
+    const int64_t n = (rows - r0 < w.chunk_rows) ? rows - r0 : w.chunk_rows;
+    GRPO_TRY(chunk_forward(dev, w, hp, wp, labels, r0, n, hidden_dim, vocab, temperature, want_ent, want_bwd,
+                           logp_out + r0, want_ent ? entropy_out + r0 : nullptr, w.lse, stream));
+    const void* mchunk = (mask_dtype == MASK_NONE) ? nullptr : static_cast<const uint8_t*>(mask) + r0 * esz;
+    token_loss_kernel<<<ew_blocks(n, 256, dev.sms), 256, 0, stream>>>(
+        logp_out + r0, old_logp + r0, advantages + r0, ref_logp ? ref_logp + r0 : nullptr,
+        want_ent ? entropy_out + r0 : nullptr, mchunk, mask_dtype, static_cast<size_t>(n), cfg, w.acc,
+        want_bwd ? w.dlogp : nullptr, (want_bwd && entropy_coef != 0.f) ? w.dent : nullptr);
+    GRPO_CUDA(cudaGetLastError());
+    if (want_bwd)
+      GRPO_TRY(chunk_backward(dev, w, hp, wp, labels, w.dlogp, entropy_coef != 0.f ? w.dent : nullptr,
+                              want_ent ? entropy_out + r0 : nullptr, w.lse, r0, n, hidden_dim, vocab, temperature,
+                              static_cast<__nv_bfloat16*>(dhidden), dweight, stream));
+  }
+  loss_finalize_kernel<<<1, 32, 0, stream>>>(w.acc, cfg, metrics);
+  GRPO_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int grpo_policy_loss_fwd_bwd(const float* logp, const float* old_logp, const float* advantages, const float* ref_logp,
+                             const void* mask, int mask_dtype, int64_t n, float clip_ratio_low, float clip_ratio_high,
+                             float clip_ratio_dual, int kl_mode, float kl_coef, float grad_accum, float* dlogp,
+                             float* metrics, double* acc_scratch, grpo_stream_t stream) {
+  if (!logp || !old_logp || !advantages || !metrics || !acc_scratch)
+    return fail(GRPO_ERR_ARG, "logp / old_logp / advantages / metrics / acc_scratch must not be null");
+  if (n < 0) return fail(GRPO_ERR_ARG, "negative length");
+  if (mask_dtype < 0 || mask_dtype > 3 || (mask_dtype != MASK_NONE && !mask))
+    return fail(GRPO_ERR_ARG, "bad mask / mask_dtype");
+  if (kl_mode < GRPO_KL_NONE || kl_mode > GRPO_KL_CHI2) return fail(GRPO_ERR_ARG, "unknown kl_mode %d", kl_mode);
+  if (kl_mode != GRPO_KL_NONE && !ref_logp) return fail(GRPO_ERR_ARG, "kl_mode set but ref_logp is null");
+  if (!(grad_accum > 0.f)) return fail(GRPO_ERR_ARG, "grad_accum must be positive");
+  LossCfg cfg = make_loss_cfg(clip_ratio_low, clip_ratio_high, clip_ratio_dual, kl_mode, kl_coef, grad_accum);
+  cfg.entropy_coef = 0.f;
+  GRPO_CUDA(cudaMemsetAsync(acc_scratch, 0, ACC_N * sizeof(double), stream));
+  if (n > 0) {
+    const uint32_t blocks = ew_blocks(n, 256, 0);
+    mask_sum_kernel<<<blocks, 256, 0, stream>>>(mask, mask_dtype, static_cast<size_t>(n), acc_scratch);
+    token_loss_kernel<<<blocks, 256, 0, stream>>>(logp, old_logp, advantages, ref_logp, nullptr, mask, mask_dtype,
+                                                  static_cast<size_t>(n), cfg, acc_scratch, dlogp, nullptr);
+  }
+  loss_finalize_kernel<<<1, 32, 0, stream>>>(acc_scratch, cfg, metrics);
+  GRPO_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int grpo_compute_kl(const float* logp, const float* ref_logp, int64_t n, int kl_mode, float* out, float* dout_dlogp,
+                    grpo_stream_t stream) {
+  if (!logp || !ref_logp || !out) return fail(GRPO_ERR_ARG, "logp / ref_logp / out must not be null");
+  if (kl_mode < GRPO_KL_LOW_VAR || kl_mode > GRPO_KL_CHI2) return fail(GRPO_ERR_ARG, "unknown kl_mode %d", kl_mode);
+  if (n <= 0) return n == 0 ? 0 : fail(GRPO_ERR_ARG, "negative length");
+  kl_elementwise_kernel<<<ew_blocks(n, 256, 0), 256, 0, stream>>>(logp, ref_logp, static_cast<size_t>(n), kl_mode, out,
+                                                                  dout_dlogp);
+  GRPO_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int grpo_masked_mean(const float* x, const void* mask, int mask_dtype, int64_t n, float eps, float* out,
+                     double* acc_scratch, grpo_stream_t stream) {
+  if (!x || !out || !acc_scratch) return fail(GRPO_ERR_ARG, "x / out / acc_scratch must not be null");
+  if (mask_dtype < 0 || mask_dtype > 3 || (mask_dtype != MASK_NONE && !mask))
+    return fail(GRPO_ERR_ARG, "bad mask / mask_dtype");
+  if (n < 0) return fail(GRPO_ERR_ARG, "negative length");
+  GRPO_CUDA(cudaMemsetAsync(acc_scratch, 0, 2 * sizeof(double), stream));
+  if (n > 0)
+    masked_sum_kernel<<<ew_blocks(n, 256, 0), 256, 0, stream>>>(x, mask, mask_dtype, static_cast<size_t>(n),
+                                                                acc_scratch);
+  masked_mean_finalize_kernel<<<1, 32, 0, stream>>>(acc_scratch, eps, out);
+  GRPO_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int grpo_advantage(const float* rewards, const void* mask, int mask_dtype, const int32_t* order,
+                   const int32_t* offsets, int64_t bsz, int64_t t_len, int64_t n_groups, float eps, float* advantages,
+                   float* seq_scratch, grpo_stream_t stream) {
+  if (!rewards || !order || !offsets || !advantages || !seq_scratch)
+    return fail(GRPO_ERR_ARG, "rewards / order / offsets / advantages / seq_scratch must not be null");
+  if (mask_dtype < 0 || mask_dtype > 3 || (mask_dtype != MASK_NONE && !mask))
+    return fail(GRPO_ERR_ARG, "bad mask / mask_dtype");
+  if (bsz < 0 || t_len < 0 || n_groups < 0 || bsz > 0x7fffffffll || t_len > 0x7fffffffll)
+    return fail(GRPO_ERR_ARG, "bad dimensions");
+  if (bsz == 0 || t_len == 0) return 0;
+  float* scores = seq_scratch;
+  float* seq_adv = seq_scratch + bsz;
+  const uint32_t b = static_cast<uint32_t>(bsz), t = static_cast<uint32_t>(t_len);
+  row_score_kernel<<<cdiv(bsz * 32, 256), 256, 0, stream>>>(rewards, b, t, scores);
+  group_stats_kernel<<<cdiv(n_groups * 32, 256), 256, 0, stream>>>(scores, order, offsets,
+                                                                   static_cast<uint32_t>(n_groups), eps, seq_adv);
+  broadcast_adv_kernel<<<ew_blocks(bsz * t_len, 256, 0), 256, 0, stream>>>(seq_adv, mask, mask_dtype, b, t,
+                                                                           advantages);
+  GRPO_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int grpo_logprob_from_logits(const void* logits, int logits_dtype, const int64_t* labels, int64_t rows, int64_t vocab,
+                             int64_t ld, float* logp, float* entropy, float* lse, grpo_stream_t stream) {
+  if (!logits || (logp && !labels)) return fail(GRPO_ERR_ARG, "logits (and labels when logp is wanted) must not be null");
+  if (rows < 0 || vocab <= 0 || ld < vocab || rows > 0x7fffffffll || vocab > 0x7fffffffll)
+    return fail(GRPO_ERR_ARG, "bad dimensions");
+  if (rows == 0) return 0;
+  const uint32_t r = static_cast<uint32_t>(rows), v = static_cast<uint32_t>(vocab);
+  const int threads = vocab >= 8192 ? 512 : 128;
+  switch (logits_dtype) {
+    case LOGITS_F32:
+      logprob_from_logits_kernel<float><<<r, threads, 0, stream>>>(static_cast<const float*>(logits), labels, r, v, ld,
+                                                                   logp, entropy, lse);
+      break;
+    case LOGITS_BF16:
+      logprob_from_logits_kernel<__nv_bfloat16><<<r, threads, 0, stream>>>(
+          static_cast<const __nv_bfloat16*>(logits), labels, r, v, ld, logp, entropy, lse);
+      break;
+    case LOGITS_F16:
+      logprob_from_logits_kernel<__half><<<r, threads, 0, stream>>>(static_cast<const __half*>(logits), labels, r, v,
+                                                                    ld, logp, entropy, lse);
+      break;
+    default: return fail(GRPO_ERR_ARG, "unknown logits dtype %d", logits_dtype);
+  }
+  GRPO_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int grpo_logprob_from_logits_bwd(const void* logits, int logits_dtype, const int64_t* labels, const float* lse,
+                                 const float* dlogp, const float* dentropy, const float* entropy, int64_t rows,
+                                 int64_t vocab, int64_t ld, void* dlogits, int64_t ld_out, grpo_stream_t stream) {
+  if (!logits || !lse || !dlogits) return fail(GRPO_ERR_ARG, "logits / lse / dlogits must not be null");
+  if (dlogp && !labels) return fail(GRPO_ERR_ARG, "dlogp needs labels");
+  if (dentropy && !entropy) return fail(GRPO_ERR_ARG, "dentropy needs the forward entropy");
+  if (rows < 0 || vocab <= 0 || ld < vocab || ld_out < vocab || rows > 0x7fffffffll || vocab > 0x7fffffffll)
+    return fail(GRPO_ERR_ARG, "bad dimensions");
+  if (rows == 0) return 0;
+  const uint32_t r = static_cast<uint32_t>(rows), v = static_cast<uint32_t>(vocab);
+  dim3 grid(cdiv(vocab, 256 * 8), r < 65535u ? r : 65535u);
+  switch (logits_dtype) {
+    case LOGITS_F32:
+      logprob_from_logits_bwd_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(logits), labels, lse,
+                                                                      dlogp, dentropy, entropy, r, v, ld,
+                                                                      static_cast<float*>(dlogits), ld_out);
+      break;
+    case LOGITS_BF16:
+      logprob_from_logits_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(
+          static_cast<const __nv_bfloat16*>(logits), labels, lse, dlogp, dentropy, entropy, r, v, ld,
+          static_cast<__nv_bfloat16*>(dlogits), ld_out);
+      break;
+    case LOGITS_F16:
+      logprob_from_logits_bwd_kernel<__half><<<grid, 256, 0, stream>>>(static_cast<const __half*>(logits), labels, lse,
+                                                                       dlogp, dentropy, entropy, r, v, ld,
+                                                                       static_cast<__half*>(dlogits), ld_out);
+      break;
+    default: return fail(GRPO_ERR_ARG, "unknown logits dtype %d", logits_dtype);
+  }
+  GRPO_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int grpo_debug_gemm(const void* a, const void* b, float* c, int64_t m, int64_t n, int64_t k, int a_mn_major,
+                    int b_mn_major, int cta_group, int accumulate, grpo_stream_t stream) {
+  if (!a || !b || !c) return fail(GRPO_ERR_ARG, "null operand");
+  if (m <= 0 || n <= 0 || k <= 0 || n % 4 != 0) return fail(GRPO_ERR_ARG, "bad dimensions (n must be a multiple of 4)");
+  if (cta_group != 1 && cta_group != 2) return fail(GRPO_ERR_ARG, "cta_group must be 1 or 2");
+  DevInfo dev;
+  GRPO_TRY(get_dev(&dev));
+  EpiF32<1, kBlockN>::Params p1{c, n, static_cast<uint32_t>(m), static_cast<uint32_t>(n),
+                                static_cast<uint32_t>(accumulate != 0)};
+  EpiF32<2, kBlockN>::Params p2{c, n, static_cast<uint32_t>(m), static_cast<uint32_t>(n),
+                                static_cast<uint32_t>(accumulate != 0)};
+  TileSched s{};
+  s.m_fast = 1;
+  const uint64_t a_pitch = a_mn_major ? m : k, b_pitch = b_mn_major ? n : k;
+  using E1 = EpiF32<1, kBlockN>;
+  using E2 = EpiF32<2, kBlockN>;
+  if (!a_mn_major && !b_mn_major)
+    return launch_gemm_any<false, false, E1, E2>(cta_group, a, m, a_pitch, b, n, b_pitch, k, s, p1, p2, dev.sms, stream);
+  if (!a_mn_major && b_mn_major)
+    return launch_gemm_any<false, true, E1, E2>(cta_group, a, m, a_pitch, b, n, b_pitch, k, s, p1, p2, dev.sms, stream);
+  if (a_mn_major && b_mn_major)
+    return launch_gemm_any<true, true, E1, E2>(cta_group, a, m, a_pitch, b, n, b_pitch, k, s, p1, p2, dev.sms, stream);
+  return launch_gemm_any<true, false, E1, E2>(cta_group, a, m, a_pitch, b, n, b_pitch, k, s, p1, p2, dev.sms, stream);
+}
+
+}  // extern "C"
