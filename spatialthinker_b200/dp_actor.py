@@ -1,0 +1,193 @@
+"""The actor's head-side micro-batch loop: drop-in for the hot part of ``verl/workers/actor/dp_actor.py``.
+
+Reference lines mirrored: ``compute_log_prob`` :170-210 (forward-only, micro-batches of
+``micro_batch_size_per_device_for_experience``), ``update_policy`` :212-292 (mini-batches of
+``global_batch_size_per_device``, GA = global // micro, per-micro-batch loss / GA, metric keys and
+``append_to_dict`` list semantics :274-290) and ``_optimizer_step`` :155-167 (clip, skip on non-finite norm).
+
+What differs by design: everything between "final hidden states" and "gradients of hidden states and lm_head weight"
+is one fused CUDA pipeline (:mod:`spatialthinker_b200.fused`), the logits tensor never exists, and the 5-6 ``.item()``
+host syncs per micro-batch (:274-286) become one device->host copy per ``update_policy`` call.
+
+The transformer body is outside this path. The actor is therefore handed either pre-computed final
+hidden states (batch key ``hidden_states``, ``[bs, response_length, H]`` - row ``t`` predicts ``responses[:, t]``,
+i.e. the ``[-T-1:-1]`` slice of dp_actor.py:139) or a ``hidden_fn(micro_batch_dict) -> hidden`` callable that runs the
+body with autograd enabled; in the second case ``dHidden`` is pushed into that graph with ``hidden.backward(...)``.
+"""
+from __future__ import annotations
+
+import os
+from collections import defaultdict
+from dataclasses import dataclass, field
+from typing import Any, Callable, Dict, List, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from .fused import fused_lm_head_log_probs, grpo_micro_batch_step
+from .sharding import allreduce_mean_
+
+__all__ = ["ActorConfig", "DataParallelPPOActor", "append_to_dict"]
+
+
+@dataclass
+class ActorConfig:
+    """The fields of the reference's ``ActorConfig`` (verl/workers/actor/config.py:69-91) that the head path reads."""
+
+    global_batch_size: int = 256
+    micro_batch_size_per_device_for_update: int = 4
+    micro_batch_size_per_device_for_experience: int = 16
+    max_grad_norm: float = 1.0
+    clip_ratio_low: float = 0.2
+    clip_ratio_high: float = 0.3
+    clip_ratio_dual: float = 3.0
+    ppo_epochs: int = 1
+    # "auto keys" filled by the trainer config's post_init in the reference (verl/trainer/config.py:99-105)
+    global_batch_size_per_device: int = -1
+    disable_kl: bool = False
+    use_kl_loss: bool = False
+    kl_penalty: str = "kl"
+    kl_coef: float = 0.0
+    # extension: 0 in the reference, where the entropy is only logged (dp_actor.py:253)
+    entropy_coeff: float = 0.0
+
+
+def append_to_dict(data: Dict[str, List[Any]], new_data: Dict[str, Any]) -> None:
+    """verl/utils/py_functional.py:65."""
+    for key, val in new_data.items():
+        data.setdefault(key, []).append(val)
+
+
+def _get(data, name):
+    return getattr(data, name) if hasattr(data, name) else data[name]
+
+
+class DataParallelPPOActor:
+    """Head-side PPO/GRPO actor. ``lm_head_weight`` is the bf16 ``[V, H]`` parameter (replicated per rank)."""
+
+    def __init__(
+        self,
+        config: ActorConfig,
+        lm_head_weight: torch.Tensor,
+        actor_optimizer: Optional[torch.optim.Optimizer] = None,
+        hidden_fn: Optional[Callable[[Dict[str, Any]], torch.Tensor]] = None,
+        process_group: Optional["dist.ProcessGroup"] = None,
+    ):
+        self.config = config
+        self.rank = int(os.getenv("RANK", "0"))
+        self.weight = lm_head_weight
+        self.actor_optimizer = actor_optimizer
+        self.hidden_fn = hidden_fn
+        self.process_group = process_group
+        self.dweight: Optional[torch.Tensor] = None  # fp32 [V, H] accumulator ("main grad") across micro-batches
+        self.last_dhidden: List[torch.Tensor] = []   # per micro-batch dHidden of the last update (when no hidden_fn)
+
+    # ------------------------------------------------------------------------------------------------------------
+    def _hidden(self, micro: Dict[str, Any], train: bool) -> torch.Tensor:
+        if "hidden_states" in micro:
+            return micro["hidden_states"]
+        if self.hidden_fn is None:
+            raise KeyError("batch has no 'hidden_states' and the actor was built without hidden_fn")
+        if train:
+            return self.hidden_fn(micro)
+        with torch.no_grad():
+            return self.hidden_fn(micro)
+
+    @staticmethod
+    def _response_mask(micro: Dict[str, Any]) -> torch.Tensor:
+        if "response_mask" in micro:
+            return micro["response_mask"]
+        response_length = micro["responses"].size(1)
+        return micro["attention_mask"][:, -response_length:]  # dp_actor.py:247
+
+    def _optimizer_step(self) -> torch.Tensor:
+        """Average dW over ranks, clip by global norm, skip a non-finite step - dp_actor.py:155-167 for the head."""
+        assert self.dweight is not None
+        allreduce_mean_(self.dweight, self.process_group)
+        grad_norm = torch.linalg.vector_norm(self.dweight)
+        if self.actor_optimizer is not None:
+            clip = torch.clamp(self.config.max_grad_norm / (grad_norm + 1e-6), max=1.0)
+            finite = torch.isfinite(grad_norm)
+            # a non-finite norm zeroes the step instead of branching on the host (the reference prints and skips)
+            scale = torch.where(finite, clip, torch.zeros_like(clip))
+            grad = (self.dweight * scale).to(self.weight.dtype)
+            grad = torch.where(finite, grad, torch.zeros_like(grad))
+            self.weight.grad = grad
+            self.actor_optimizer.step()
+            self.actor_optimizer.zero_grad()
+        self.dweight.zero_()
+        return grad_norm
+
+    # ------------------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def compute_log_prob(self, data) -> torch.Tensor:
+        """Log-probs of the responses, ``[bs, response_length]`` fp32 - dp_actor.py:170-210 (old / ref log-probs)."""
+        temperature = _get(data, "meta_info")["temperature"]
+        keys = ["responses"] + [k for k in ("hidden_states", "input_ids", "attention_mask", "position_ids")
+                                if k in _get(data, "batch")]
+        outs = []
+        for mb in data.select(keys).split(self.config.micro_batch_size_per_device_for_experience):
+            micro = {**mb.batch, **mb.non_tensor_batch}
+            hidden = self._hidden(micro, train=False)
+            logp, _ = fused_lm_head_log_probs(hidden, self.weight.detach(), micro["responses"], temperature)
+            outs.append(logp)
+        return torch.concat(outs, dim=0)
+
+    def update_policy(self, data) -> Dict[str, Any]:
+        """dp_actor.py:212-292: returns the reference's metrics dict (lists per micro-batch / per optimizer step)."""
+        cfg = self.config
+        temperature = _get(data, "meta_info")["temperature"]  # must be present, as in the reference (:215)
+        use_ref = cfg.use_kl_loss and not cfg.disable_kl
+        keys = ["responses", "old_log_probs", "advantages"]
+        keys += [k for k in ("hidden_states", "input_ids", "attention_mask", "position_ids", "response_mask")
+                 if k in _get(data, "batch")]
+        if use_ref:
+            keys.append("ref_log_probs")
+        mini_batches = data.select(keys).split(cfg.global_batch_size_per_device)
+
+        if self.dweight is None:
+            self.dweight = torch.zeros(self.weight.shape, dtype=torch.float32, device=self.weight.device)
+        pending: List[torch.Tensor] = []  # device metric vectors, one per micro-batch
+        norms: List[torch.Tensor] = []
+        self.last_dhidden = []
+        for _ in range(cfg.ppo_epochs):
+            for mini_batch in mini_batches:
+                grad_accum = cfg.global_batch_size_per_device // cfg.micro_batch_size_per_device_for_update
+                for mb in mini_batch.split(cfg.micro_batch_size_per_device_for_update):
+                    micro = {**mb.batch, **mb.non_tensor_batch}
+                    hidden = self._hidden(micro, train=True)
+                    step = grpo_micro_batch_step(
+                        hidden.detach(), self.weight.detach(), micro["responses"], micro["old_log_probs"],
+                        micro["advantages"], micro["ref_log_probs"] if use_ref else None, self._response_mask(micro),
+                        temperature=temperature, clip_ratio_low=cfg.clip_ratio_low, clip_ratio_high=cfg.clip_ratio_high,
+                        clip_ratio_dual=cfg.clip_ratio_dual, kl_penalty=cfg.kl_penalty if use_ref else None,
+                        kl_coef=cfg.kl_coef, grad_accum=float(grad_accum), entropy_coeff=cfg.entropy_coeff,
+                        dweight_accum=self.dweight,
+                    )
+                    if hidden.requires_grad:
+                        hidden.backward(step["dhidden"])  # continue into the transformer body
+                    else:
+                        self.last_dhidden.append(step["dhidden"])
+                    pending.append(step["metrics"])
+                norms.append(self._optimizer_step())
+
+        # one device->host transfer for every scalar of this call
+        host = torch.stack(pending).float().cpu() if pending else torch.zeros(0, _lib.NUM_METRICS)
+        host_norms = torch.stack(norms).float().cpu().tolist() if norms else []
+        metrics: Dict[str, Any] = defaultdict(list)
+        per_step = len(pending) // max(len(norms), 1)
+        for i, row in enumerate(host.tolist()):
+            if use_ref:  # the reference ASSIGNS these two (dp_actor.py:274-275): last micro-batch wins
+                metrics["actor/kl_loss"] = row[_lib.MET_KL_LOSS]
+                metrics["actor/kl_coef"] = cfg.kl_coef
+            append_to_dict(metrics, {
+                "actor/pg_loss": row[_lib.MET_TOTAL],
+                "actor/pg_clipfrac_higher": row[_lib.MET_CLIPFRAC_HI],
+                "actor/pg_clipfrac_lower": row[_lib.MET_CLIPFRAC_LO],
+                "actor/entropy_loss": row[_lib.MET_ENTROPY],
+                "actor/ppo_kl": row[_lib.MET_PPO_KL],
+            })
+            if per_step and (i + 1) % per_step == 0:
+                append_to_dict(metrics, {"actor/grad_norm": host_norms[(i + 1) // per_step - 1]})
+        return metrics

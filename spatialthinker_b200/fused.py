@@ -1,0 +1,275 @@
+"""Fused lm_head entry points: the logits tensor ``[tokens, vocab]`` is never materialised.
+
+The reference reaches this arithmetic through three separate stages - HF ``lm_head`` (cuBLAS, logits written to HBM),
+``logits.div_(temperature)`` and flash-attn's Triton cross-entropy (dp_actor.py:118-128, torch_functional.py:34-66) -
+followed by ~25 elementwise kernels for the loss (core_algos.py:291-353, 394-436) and autograd's three backward
+passes over the logits. A ``logits`` argument cannot be fused with the GEMM that produces it, so these functions take
+the final hidden states and the ``lm_head`` weight instead:
+
+* :func:`fused_lm_head_log_probs` - hidden, weight, labels -> log-probs (and entropy), differentiable.
+* :func:`fused_grpo_loss` - one micro-batch of dp_actor.py:247-278: log-probs, clipped policy loss, KL term, masked
+  means, and the gradients into hidden and weight, in a single pass of three GEMM units.
+* :func:`grpo_micro_batch_step` - the same without autograd, accumulating ``dW`` straight into an fp32 buffer; this is
+  what :mod:`spatialthinker_b200.dp_actor` loops over.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._util import f32c, mask_arg, require_cuda, scratch
+
+
+def _check_head(hidden: torch.Tensor, weight: torch.Tensor, labels: torch.Tensor):
+    dev = require_cuda(hidden, weight, labels)
+    if hidden.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16:
+        raise ValueError("hidden and weight must be bfloat16 (the actor's parameter dtype, actor/config.py:57)")
+    if weight.dim() != 2 or hidden.shape[-1] != weight.shape[1]:
+        raise ValueError(f"weight {tuple(weight.shape)} does not match hidden {tuple(hidden.shape)}")
+    if labels.shape != hidden.shape[:-1]:
+        raise ValueError(f"labels {tuple(labels.shape)} do not match hidden {tuple(hidden.shape)}")
+    h2 = hidden.contiguous().view(-1, hidden.shape[-1])
+    w2 = weight.contiguous()
+    lab = labels.contiguous().view(-1).to(torch.int64)
+    return dev, h2, w2, lab
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# log-probs with autograd
+# ----------------------------------------------------------------------------------------------------------------
+class _FusedLogProbs(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, hidden, weight, labels, temperature: float, want_entropy: bool):
+        dev, h2, w2, lab = _check_head(hidden, weight, labels)
+        lib = _lib.load()
+        rows, hdim = h2.shape
+        vocab = w2.shape[0]
+        logp = torch.empty(rows, dtype=torch.float32, device=dev)
+        ent = torch.empty(rows, dtype=torch.float32, device=dev) if want_entropy else None
+        nbytes = lib.grpo_lmhead_fwd_workspace_bytes(rows, hdim, vocab)
+        ws = scratch("head", dev, nbytes)
+        with torch.cuda.device(dev):
+            _lib.check(
+                lib.grpo_lmhead_logprob_fwd(h2.data_ptr(), w2.data_ptr(), lab.data_ptr(), rows, hdim, vocab,
+                                            float(temperature), logp.data_ptr(), _lib.ptr(ent), None, ws.data_ptr(),
+                                            ws.numel(), _lib.stream_ptr(dev)),
+                "grpo_lmhead_logprob_fwd",
+            )
+        ctx.save_for_backward(h2, w2, lab)
+        ctx.temperature = float(temperature)
+        ctx.hshape, ctx.wdtype = hidden.shape, weight.dtype
+        ctx.want_entropy = want_entropy
+        lead = hidden.shape[:-1]
+        return logp.view(*lead), (ent.view(*lead) if want_entropy else None)
+
+    @staticmethod
+    def backward(ctx, g_logp, g_ent):
+        h2, w2, lab = ctx.saved_tensors
+        lib = _lib.load()
+        dev = h2.device
+        rows, hdim = h2.shape
+        vocab = w2.shape[0]
+        gl = f32c(g_logp.reshape(-1)) if g_logp is not None else torch.zeros(rows, dtype=torch.float32, device=dev)
+        ge = f32c(g_ent.reshape(-1)) if (g_ent is not None and ctx.want_entropy) else None
+        dh = torch.empty(rows, hdim, dtype=torch.bfloat16, device=dev)
+        dw = torch.zeros(vocab, hdim, dtype=torch.float32, device=dev)
+        nbytes = lib.grpo_lmhead_bwd_workspace_bytes(rows, hdim, vocab)
+        ws = scratch("head", dev, nbytes)
+        with torch.cuda.device(dev):
+            _lib.check(
+                lib.grpo_lmhead_bwd(h2.data_ptr(), w2.data_ptr(), lab.data_ptr(), gl.data_ptr(), _lib.ptr(ge), rows,
+                                    hdim, vocab, ctx.temperature, dh.data_ptr(), dw.data_ptr(), ws.data_ptr(),
+                                    ws.numel(), _lib.stream_ptr(dev)),
+                "grpo_lmhead_bwd",
+            )
+        return dh.view(ctx.hshape), dw.to(ctx.wdtype), None, None, None
+
+
+def fused_lm_head_log_probs(
+    hidden: torch.Tensor, weight: torch.Tensor, labels: torch.Tensor, temperature: float = 1.0, want_entropy: bool = False
+) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """``log_softmax(hidden @ weight.T / temperature)[labels]`` (and the entropy of that softmax) without the logits.
+
+    hidden ``[..., H]`` bf16, weight ``[V, H]`` bf16, labels ``[...]`` int64 -> (log-probs ``[...]`` fp32,
+    entropy ``[...]`` fp32 or None). Differentiable with respect to ``hidden`` and ``weight``; the backward recomputes
+    the logits tiles chunk by chunk (4 GEMM units in total). Forward-only use (``compute_log_prob``,
+    dp_actor.py:170-210) is a single GEMM unit.
+    """
+    return _FusedLogProbs.apply(hidden, weight, labels, temperature, want_entropy)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# one micro-batch of the actor update, no autograd
+# ----------------------------------------------------------------------------------------------------------------
+METRIC_KEYS = {
+    "actor/pg_loss": _lib.MET_TOTAL,  # reported after the KL term was added, dp_actor.py:271,281
+    "actor/pg_clipfrac_higher": _lib.MET_CLIPFRAC_HI,
+    "actor/pg_clipfrac_lower": _lib.MET_CLIPFRAC_LO,
+    "actor/entropy_loss": _lib.MET_ENTROPY,
+    "actor/ppo_kl": _lib.MET_PPO_KL,
+}
+
+
+def grpo_micro_batch_step(
+    hidden: torch.Tensor,
+    weight: torch.Tensor,
+    labels: torch.Tensor,
+    old_log_probs: torch.Tensor,
+    advantages: torch.Tensor,
+    ref_log_probs: Optional[torch.Tensor],
+    response_mask: torch.Tensor,
+    *,
+    temperature: float = 1.0,
+    clip_ratio_low: float = 0.2,
+    clip_ratio_high: float = 0.3,
+    clip_ratio_dual: float = 3.0,
+    kl_penalty: Optional[str] = "low_var_kl",
+    kl_coef: float = 0.0,
+    grad_accum: float = 1.0,
+    entropy_coeff: float = 0.0,
+    want_entropy: bool = False,
+    dweight_accum: Optional[torch.Tensor] = None,
+    need_grads: bool = True,
+) -> Dict[str, torch.Tensor]:
+    """Forward + backward of one micro-batch (dp_actor.py:247-278) entirely on the device, no host sync.
+
+    Returns a dict of device tensors: ``log_probs`` [.. ] fp32, ``entropy`` (or None), ``metrics`` (fp32 vector indexed
+    by the ``_lib.MET_*`` slots), ``dhidden`` (bf16, gradient of ``loss = total / grad_accum``) and ``dweight`` - the
+    fp32 ``[V, H]`` buffer the weight gradient was ACCUMULATED into (``dweight_accum`` if given, else a fresh zero
+    buffer).
+    """
+    dev, h2, w2, lab = _check_head(hidden, weight, labels)
+    lib = _lib.load()
+    rows, hdim = h2.shape
+    vocab = w2.shape[0]
+    lead = hidden.shape[:-1]
+    for name, t in (("old_log_probs", old_log_probs), ("advantages", advantages), ("response_mask", response_mask)):
+        if t.shape != lead:
+            raise ValueError(f"{name} {tuple(t.shape)} does not match the token layout {tuple(lead)}")
+    use_kl = ref_log_probs is not None and kl_penalty is not None
+    mode = _lib.KL_MODES.get(kl_penalty, None) if use_kl else -1
+    if mode is None:
+        raise NotImplementedError(f"Unknown KL penalty: {kl_penalty}.")
+    old, adv = f32c(old_log_probs).view(-1), f32c(advantages).view(-1)
+    ref = f32c(ref_log_probs).view(-1) if use_kl else None
+    mask, code = mask_arg(response_mask)
+    want_entropy = want_entropy or entropy_coeff != 0.0
+    logp = torch.empty(rows, dtype=torch.float32, device=dev)
+    ent = torch.empty(rows, dtype=torch.float32, device=dev) if want_entropy else None
+    metrics = torch.empty(_lib.NUM_METRICS, dtype=torch.float32, device=dev)
+    dh = dw = None
+    if need_grads:
+        dh = torch.empty(rows, hdim, dtype=torch.bfloat16, device=dev)
+        if dweight_accum is not None:
+            if dweight_accum.shape != w2.shape or dweight_accum.dtype != torch.float32 or not dweight_accum.is_contiguous():
+                raise ValueError("dweight_accum must be a contiguous float32 tensor shaped like weight")
+            dw = dweight_accum
+        else:
+            dw = torch.zeros(vocab, hdim, dtype=torch.float32, device=dev)
+    nbytes = lib.grpo_fused_loss_workspace_bytes(rows, hdim, vocab)
+    ws = scratch("head", dev, nbytes)
+    with torch.cuda.device(dev):
+        _lib.check(
+            lib.grpo_fused_loss_fwd_bwd(
+                h2.data_ptr(), w2.data_ptr(), lab.data_ptr(), old.data_ptr(), adv.data_ptr(), _lib.ptr(ref),
+                mask.data_ptr(), code, rows, hdim, vocab, float(temperature), float(clip_ratio_low),
+                float(clip_ratio_high), float(clip_ratio_dual), mode, float(kl_coef if use_kl else 0.0),
+                float(entropy_coeff), float(grad_accum), logp.data_ptr(), _lib.ptr(ent), _lib.ptr(dh), _lib.ptr(dw),
+                metrics.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev)),
+            "grpo_fused_loss_fwd_bwd",
+        )
+    return {
+        "log_probs": logp.view(*lead),
+        "entropy": ent.view(*lead) if ent is not None else None,
+        "metrics": metrics,
+        "dhidden": dh.view(hidden.shape) if dh is not None else None,
+        "dweight": dw,
+        "used_kl": use_kl,
+    }
+
+
+def metrics_to_dict(metrics: torch.Tensor, used_kl: bool, kl_coef: float) -> Dict[str, float]:
+    """ONE device->host read for all of a micro-batch's ``actor/*`` scalars (the reference does 5-6 ``.item()`` syncs
+    per micro-batch, dp_actor.py:274-286)."""
+    host = metrics.detach().float().cpu().tolist()
+    out = {key: host[slot] for key, slot in METRIC_KEYS.items()}
+    if used_kl:
+        out["actor/kl_loss"] = host[_lib.MET_KL_LOSS]
+        out["actor/kl_coef"] = kl_coef
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# the same with autograd
+# ----------------------------------------------------------------------------------------------------------------
+class _FusedGrpoLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, hidden, weight, labels, old_log_probs, advantages, ref_log_probs, response_mask, kw):
+        need = hidden.requires_grad or weight.requires_grad
+        res = grpo_micro_batch_step(hidden, weight, labels, old_log_probs, advantages, ref_log_probs, response_mask,
+                                    need_grads=need, **kw)
+        if need:
+            ctx.save_for_backward(res["dhidden"], res["dweight"])
+        ctx.wdtype = weight.dtype
+        ctx.need = need
+        m = res["metrics"]
+        ctx.mark_non_differentiable(m, res["log_probs"])
+        ent = res["entropy"]
+        if ent is not None:
+            ctx.mark_non_differentiable(ent)
+        ctx.used_kl = res["used_kl"]
+        return m[_lib.MET_SCALED].clone(), m, res["log_probs"], ent
+
+    @staticmethod
+    def backward(ctx, g_loss, g_m, g_lp, g_ent):
+        if not ctx.need:
+            return (None,) * 8
+        dh, dw = ctx.saved_tensors
+        # gradients were produced in the forward pass for d(loss) = 1; apply the upstream scalar here
+        return (dh.float() * g_loss).to(dh.dtype), (dw * g_loss).to(ctx.wdtype), None, None, None, None, None, None
+
+
+def fused_grpo_loss(
+    hidden: torch.Tensor,
+    weight: torch.Tensor,
+    labels: torch.Tensor,
+    old_log_probs: torch.Tensor,
+    advantages: torch.Tensor,
+    ref_log_probs: Optional[torch.Tensor],
+    response_mask: torch.Tensor,
+    *,
+    temperature: float = 1.0,
+    clip_ratio_low: float = 0.2,
+    clip_ratio_high: float = 0.3,
+    clip_ratio_dual: float = 3.0,
+    kl_penalty: Optional[str] = "low_var_kl",
+    kl_coef: float = 0.0,
+    grad_accum: float = 1.0,
+    entropy_coeff: float = 0.0,
+    want_entropy: bool = False,
+) -> Tuple[torch.Tensor, Dict[str, torch.Tensor]]:
+    """One micro-batch of the actor update as a differentiable scalar.
+
+    ``loss = (pg_loss + kl_coef * masked_mean(kl) - entropy_coeff * masked_mean(entropy)) / grad_accum`` with the
+    reference's per-micro-batch masked means (dp_actor.py:253-277). ``loss.backward()`` delivers the gradients that
+    were already produced in the forward pass (three GEMM units in total, nothing recomputed).
+
+    Returns ``(loss, metrics)``; ``metrics`` holds 0-d device tensors under the reference's ``actor/*`` keys
+    (dp_actor.py:274-286) plus ``log_probs`` (and ``entropy`` when requested). Nothing is copied to the host.
+    """
+    kw = dict(temperature=temperature, clip_ratio_low=clip_ratio_low, clip_ratio_high=clip_ratio_high,
+              clip_ratio_dual=clip_ratio_dual, kl_penalty=kl_penalty, kl_coef=kl_coef, grad_accum=grad_accum,
+              entropy_coeff=entropy_coeff, want_entropy=want_entropy)
+    loss, m, logp, ent = _FusedGrpoLoss.apply(hidden, weight, labels, old_log_probs, advantages, ref_log_probs,
+                                              response_mask, kw)
+    metrics = {key: m[slot] for key, slot in METRIC_KEYS.items()}
+    if ref_log_probs is not None and kl_penalty is not None:
+        metrics["actor/kl_loss"] = m[_lib.MET_KL_LOSS]
+        metrics["actor/kl_coef"] = kl_coef
+    metrics["log_probs"] = logp
+    if ent is not None:
+        metrics["entropy"] = ent
+        metrics["actor/entropy"] = m[_lib.MET_TRUE_ENTROPY]
+    return loss, metrics

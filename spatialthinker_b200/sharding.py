@@ -1,0 +1,124 @@
+"""Sharding of the GRPO hot path over the GPUs of one NVSwitch box: one process per GPU, sequences are the unit.
+
+* The ``lm_head`` weight is replicated; each rank owns an equal number of rollout sequences, token-balanced with the
+  largest-differencing method - the same policy the reference's driver applies before dispatch
+  (``_balance_batch`` ray_trainer.py:526-541 -> ``get_seqlen_balanced_partitions`` seqlen_balancing.py:150-181).
+* Advantages need every sequence's score (groups straddle ranks after balancing): scores are all-gathered
+  (``B`` floats) and the group statistics run redundantly per rank.
+* The only data-path collective is the mean all-reduce of ``dW_lm_head`` (fp32, once per optimizer step), matching
+  FSDP's gradient averaging with ``mp_reduce_dtype = fp32`` (actor/config.py:58).
+"""
+from __future__ import annotations
+
+import heapq
+from typing import List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# token-balanced partition of sequences
+# ----------------------------------------------------------------------------------------------------------------
+def balanced_partitions(seqlens: Sequence[int], k: int, equal_size: bool = True) -> List[List[int]]:
+    """Split item indices into ``k`` parts with near-equal length sums (Karmarkar-Karp largest differencing).
+
+    ``equal_size=True`` additionally forces the same number of items per part (``len(seqlens) % k == 0``), which is
+    what the dispatch to data-parallel ranks needs. Each returned part is sorted by index, like
+    seqlen_balancing.py:165-176.
+    """
+    n = len(seqlens)
+    assert n >= k, f"number of items:[{n}] < k_partitions:[{k}]"
+    # A partial solution is a list of k bins, kept sorted by descending (sum, count, items); two solutions are merged
+    # by pairing the heaviest bin of one with the lightest of the other. The heap pops the solution with the largest
+    # spread (heaviest - lightest) first.
+    def bin_key(b):
+        return (b[0], len(b[1]), b[1])
+
+    def make_state(items):
+        bins = [(0, [])] * k
+        bins = [(length, [(idx, length)]) for idx, length in items] + [(0, []) for _ in range(k - len(items))]
+        bins.sort(key=bin_key, reverse=True)
+        return bins
+
+    def heap_entry(bins, serial):
+        spread = bins[0][0] - bins[-1][0]
+        top = bin_key(bins[0])
+        # max-spread first, then the state whose heaviest bin is larger; `serial` keeps comparisons total
+        return (-spread, _Reversed(top), serial, bins)
+
+    by_len = sorted((int(length), idx) for idx, length in enumerate(seqlens))
+    heap = []
+    serial = 0
+    if equal_size:
+        assert n % k == 0, f"{n} % {k} != 0"
+        for off in range(0, n, k):
+            items = [(idx, length) for length, idx in by_len[off:off + k]]
+            heapq.heappush(heap, heap_entry(make_state(items), serial))
+            serial += 1
+    else:
+        for length, idx in by_len:
+            heapq.heappush(heap, heap_entry(make_state([(idx, length)]), serial))
+            serial += 1
+    while len(heap) > 1:
+        a = heapq.heappop(heap)[3]
+        b = heapq.heappop(heap)[3]
+        merged = [(a[i][0] + b[k - 1 - i][0], a[i][1] + b[k - 1 - i][1]) for i in range(k)]
+        merged.sort(key=bin_key, reverse=True)
+        heapq.heappush(heap, heap_entry(merged, serial))
+        serial += 1
+    parts = [sorted(idx for idx, _ in items) for _, items in heap[0][3]]
+    seen = sorted(i for p in parts for i in p)
+    assert seen == list(range(n)) and all(len(p) > 0 for p in parts)
+    if equal_size:
+        assert all(len(p) * k == n for p in parts)
+    return parts
+
+
+class _Reversed:
+    """Wrap a key so that larger compares as smaller (heapq is a min-heap)."""
+    __slots__ = ("key",)
+
+    def __init__(self, key):
+        self.key = key
+
+    def __lt__(self, other):
+        return self.key > other.key
+
+    def __eq__(self, other):
+        return self.key == other.key
+
+
+def rank_rows(seqlens: Sequence[int], world_size: int, rank: int) -> List[int]:
+    """Row ids this rank owns after token-balancing (equal sequence counts)."""
+    return balanced_partitions(seqlens, world_size, equal_size=True)[rank]
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# collectives
+# ----------------------------------------------------------------------------------------------------------------
+def _world(group=None) -> int:
+    return dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+
+
+def allreduce_mean_(grad: torch.Tensor, group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
+    """In-place mean all-reduce of the fp32 ``dW_lm_head`` accumulator over the data-parallel ranks."""
+    ws = _world(group)
+    if ws == 1:
+        return grad
+    if dist.get_backend(group) == "nccl":
+        dist.all_reduce(grad, op=dist.ReduceOp.AVG, group=group)
+    else:  # gloo (CPU tests) has no AVG
+        dist.all_reduce(grad, op=dist.ReduceOp.SUM, group=group)
+        grad.div_(ws)
+    return grad
+
+
+def all_gather_rows(local: torch.Tensor, group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
+    """Concatenate equally-sized per-rank row blocks (sequence scores, uid codes) in rank order."""
+    ws = _world(group)
+    if ws == 1:
+        return local
+    out = [torch.empty_like(local) for _ in range(ws)]
+    dist.all_gather(out, local.contiguous(), group=group)
+    return torch.cat(out, dim=0)

@@ -1,0 +1,478 @@
+"""Parity of the CUDA path (through the Python mirror of the reference interface and the C ABI underneath) against
+the CPU oracle and the golden vectors generated from the reference.
+
+Tolerances are the ones BASELINE.json's north_star states: per-token log-probs and entropy 2e-3 absolute,
+advantages 1e-6 (|a - a_ref| <= 1e-6 * max(1, |a_ref|)), loss and gradients 1e-2 relative (Frobenius for tensors).
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import grpo_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+CLIP = (0.2, 0.3, 3.0)
+TOL_LOGP = 2e-3
+TOL_ADV = 1e-6
+TOL_REL = 1e-2
+
+
+@pytest.fixture(scope="module")
+def st():
+    import spatialthinker_b200 as st
+
+    st.load_library()
+    return st
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+def rel(a: torch.Tensor, b: torch.Tensor) -> float:
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def t(x):
+    return torch.from_numpy(np.asarray(x))
+
+
+def adv_close(got, want):
+    got, want = got.detach().cpu(), want.detach().cpu()
+    assert bool(((got - want).abs() <= TOL_ADV * want.abs().clamp_min(1.0)).all()), float((got - want).abs().max())
+
+
+# ================================================================================================ tcgen05 GEMM
+@pytest.mark.parametrize("cta", [1, 2])
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 1), (1, 0)])
+def test_debug_gemm_layouts(st, dev, cta, a_mn, b_mn):
+    from spatialthinker_b200 import _lib
+
+    lib = _lib.load()
+    m, n, k = 648, 776, 456  # ragged in every dimension (multiples of 8 for the 16-byte TMA pitch)
+    g = torch.Generator().manual_seed(m + 7 * cta)
+    a = torch.randn(m, k, generator=g).to(torch.bfloat16)
+    b = torch.randn(n, k, generator=g).to(torch.bfloat16)
+    want = a.double() @ b.double().t()
+    a_d = (a.t().contiguous() if a_mn else a).to(dev)
+    b_d = (b.t().contiguous() if b_mn else b).to(dev)
+    c = torch.full((m, n), 3.0, device=dev)
+    _lib.check(lib.grpo_debug_gemm(a_d.data_ptr(), b_d.data_ptr(), c.data_ptr(), m, n, k, a_mn, b_mn, cta, 1,
+                                   _lib.stream_ptr(dev)), "gemm")
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(c.cpu().double().numpy(), (want + 3.0).numpy(), rtol=0, atol=2e-3)
+
+
+# ================================================================================================ logits surface
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+def test_log_probs_from_logits(st, dev, dtype):
+    g = torch.Generator().manual_seed(0)
+    z = (3 * torch.randn(5, 37, 1000, generator=g)).to(dtype)
+    lab = torch.randint(0, 1000, (5, 37), generator=g)
+    want = O.log_probs_from_logits(z.float(), lab)
+    zd = z.to(dev).requires_grad_(True)
+    got = st.log_probs_from_logits(zd, lab.to(dev))
+    assert got.shape == (5, 37) and got.dtype == torch.float32 and bool((got <= 0).all())
+    assert float((got.cpu() - want).abs().max()) < 1e-4
+    assert st.logprobs_from_logits is st.log_probs_from_logits
+    # backward: d/dz sum(w * logp)
+    w = torch.randn(5, 37, generator=g)
+    (got * w.to(dev)).sum().backward()
+    zr = z.float().requires_grad_(True)
+    (O.log_probs_from_logits(zr, lab) * w).sum().backward()
+    assert rel(zd.grad, zr.grad) < (1e-5 if dtype == torch.float32 else 6e-3)
+    assert float(zd.grad.float().sum(-1).abs().max()) < 2e-2  # sum_v dL/dz = 0
+
+
+def test_entropy_from_logits(st, dev):
+    g = torch.Generator().manual_seed(1)
+    z = 4 * torch.randn(64, 151936 // 8, generator=g)
+    zd = z.to(dev).requires_grad_(True)
+    ent = st.entropy_from_logits(zd)
+    want = O.entropy_from_logits(z)
+    assert float((ent.cpu() - want).abs().max()) < 1e-4
+    assert bool((ent >= 0).all()) and bool((ent <= math.log(z.shape[-1]) + 1e-4).all())
+    ent.sum().backward()
+    zr = z.clone().requires_grad_(True)
+    O.entropy_from_logits(zr).sum().backward()
+    assert rel(zd.grad, zr.grad) < 1e-4
+
+
+def test_logits_edge_cases(st, dev):
+    # odd vocab (scalar path), unaligned rows, single row, empty batch
+    g = torch.Generator().manual_seed(2)
+    z = torch.randn(3, 1001, generator=g)
+    lab = torch.tensor([0, 1000, 500])
+    got = st.log_probs_from_logits(z.to(dev), lab.to(dev))
+    assert float((got.cpu() - O.log_probs_from_logits(z, lab)).abs().max()) < 1e-5
+    empty = st.log_probs_from_logits(torch.zeros(0, 16, device=dev), torch.zeros(0, dtype=torch.int64, device=dev))
+    assert empty.shape == (0,)
+    with pytest.raises(ValueError):
+        st.log_probs_from_logits(torch.zeros(2, 16, device=dev), torch.zeros(3, dtype=torch.int64, device=dev))
+
+
+def test_masked_mean(st, dev, golden):
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(7, 300, generator=g)
+    for mask in ((torch.rand(7, 300, generator=g) > 0.4).long(), (torch.rand(7, 300, generator=g) > 0.4).float(),
+                 torch.rand(7, 300, generator=g) > 0.4):
+        got = st.masked_mean(x.to(dev), mask.to(dev))
+        want = O.masked_mean(x, mask.float() if mask.dtype == torch.bool else mask)
+        assert abs(float(got) - float(want)) < 1e-6
+        np.testing.assert_allclose(st.masked_mean(x.to(dev), mask.to(dev), dim=-1).cpu().numpy(),
+                                   O.masked_mean(x, mask.float(), dim=-1).numpy(), rtol=1e-5, atol=1e-6)
+    assert float(st.masked_mean(torch.ones(3, 4, device=dev), torch.zeros(3, 4, device=dev))) == 0.0  # KAT-D
+    xd = x.to(dev).requires_grad_(True)
+    m = (torch.rand(7, 300, generator=g) > 0.5).long()
+    st.masked_mean(xd, m.to(dev)).backward()
+    np.testing.assert_allclose(xd.grad.cpu().numpy(), (m.float() / m.sum()).numpy(), rtol=1e-6)
+
+
+# ================================================================================================ core_algos surface
+@pytest.mark.parametrize("mode", O.KL_MODES)
+def test_compute_kl_golden(st, dev, golden, mode):
+    g = golden("policy_loss")
+    lp = t(g["kl_logp"]).to(dev).requires_grad_(True)
+    out = st.compute_kl(lp, t(g["kl_ref"]).to(dev), mode)
+    out.sum().backward()
+    np.testing.assert_allclose(out.detach().cpu().numpy(), g[f"kl_{mode}"], rtol=2e-6, atol=1e-6)
+    np.testing.assert_allclose(lp.grad.cpu().numpy(), g[f"kl_{mode}_grad"], rtol=2e-6, atol=1e-6)
+    assert st.kl_penalty(lp.detach(), t(g["kl_ref"]).to(dev), mode).shape == lp.shape
+
+
+def test_policy_loss_golden(st, dev, golden):
+    g = golden("policy_loss")
+    lp = t(g["a_logp"]).to(dev).requires_grad_(True)
+    res = st.compute_policy_loss(t(g["a_old"]).to(dev), lp, t(g["a_adv"]).to(dev), t(g["a_mask"]).to(dev), *CLIP)
+    res[0].backward()
+    np.testing.assert_allclose([float(r) for r in res], g["a_out"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(lp.grad.cpu().numpy(), g["a_grad"], rtol=1e-6, atol=1e-8)
+
+
+def test_policy_loss_seeded_vs_oracle(st, dev):
+    g = torch.Generator().manual_seed(4)
+    bsz, tl = 16, 700
+    lp = -3 * torch.rand(bsz, tl, generator=g)
+    old = O.perturbed_log_probs(lp, seed=1, jitter=0.2, outlier_frac=0.05)
+    adv = torch.randn(bsz, 1, generator=g).expand(bsz, tl).contiguous()
+    lens = torch.randint(1, tl + 1, (bsz,), generator=g)
+    mask = (torch.arange(tl)[None] < lens[:, None]).long()
+    lpr = lp.clone().requires_grad_(True)
+    want = O.compute_policy_loss(old, lpr, adv, mask, *CLIP)
+    (want[0] + 0.3 * want[3]).backward()
+    lpd = lp.to(dev).requires_grad_(True)
+    got = st.compute_policy_loss(old.to(dev), lpd, adv.to(dev), mask.to(dev), *CLIP)
+    (got[0] + 0.3 * got[3]).backward()
+    for a, b in zip(got, want):
+        assert abs(float(a) - float(b)) <= 1e-5 * max(1.0, abs(float(b)))
+    assert float(want[1]) > 0 and float(want[2]) > 0  # both clip sides and the dual clip are exercised
+    assert rel(lpd.grad, lpr.grad) < 1e-5
+    # on-policy: ratio 1 => nothing clipped, ppo_kl 0
+    res = st.compute_policy_loss(lp.to(dev), lp.to(dev), adv.to(dev), mask.to(dev), *CLIP)
+    assert float(res[1]) == 0 and float(res[2]) == 0 and float(res[3]) == 0
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c", "d"])
+def test_advantage_golden(st, dev, golden, tag):
+    g = golden("advantage")
+    uid = np.array([str(u) for u in g[f"{tag}_uid"]], dtype=object)
+    adv, ret = st.compute_grpo_outcome_advantage(t(g[f"{tag}_rewards"]).to(dev), t(g[f"{tag}_mask"]).to(dev), uid)
+    assert adv is ret and adv.dtype == torch.float32
+    adv_close(adv, t(g[f"{tag}_adv"]))
+
+
+def test_advantage_full_size_vs_oracle(st, dev):
+    # config C3's batch: 512 prompts x n=8 = 4096 sequences, T=1024, permuted groups, ragged masks
+    roll = O.synth_rollout(4096, 1024, 151936, 8, seed=9, ragged=True)
+    want, _ = O.compute_grpo_outcome_advantage(roll["token_level_rewards"].clone(), roll["response_mask"], roll["uid"])
+    got, _ = st.compute_grpo_outcome_advantage(roll["token_level_rewards"].to(dev), roll["response_mask"].to(dev), roll["uid"])
+    adv_close(got, want)
+    # float and bool masks, n = 16
+    roll = O.synth_rollout(512, 77, 1000, 16, seed=10, ragged=True)
+    want, _ = O.compute_grpo_outcome_advantage(roll["token_level_rewards"].clone(), roll["response_mask"], roll["uid"])
+    for m in (roll["response_mask"].float(), roll["response_mask"].bool()):
+        got, _ = st.compute_grpo_outcome_advantage(roll["token_level_rewards"].to(dev), m.to(dev), roll["uid"])
+        adv_close(got, want)
+    with pytest.raises(AssertionError):
+        st.compute_grpo_outcome_advantage(torch.ones(3, 2, device=dev), torch.ones(3, 2, device=dev),
+                                          np.array(["a", "a", "b"], dtype=object))
+
+
+# ================================================================================================ fused lm_head
+HEAD_CASES = [
+    # rows, H, V, sigma_w, temperature
+    (300, 256, 2176, 0.02, 1.0),       # ragged rows, vocab tail tile of 128
+    (1000, 512, 151936, 0.16, 0.7),    # Qwen2.5 vocab, peaked logits (std ~ 5, max ~ 25)
+    (515, 128, 152064, 0.3, 1.3),      # HF-padded 7B vocab, very peaked
+    (129, 64, 1000, 0.05, 1.0),        # vocab not a multiple of 32 (masked tail columns)
+]
+
+
+@pytest.mark.parametrize("rows,h,v,sigma,temp", HEAD_CASES)
+def test_fused_log_probs_forward(st, dev, rows, h, v, sigma, temp):
+    hid, w = O.synth_head(rows, h, v, seed=rows, sigma_w=sigma)
+    lab = torch.randint(0, v, (rows,), generator=torch.Generator().manual_seed(rows))
+    want_lp, want_ent = O.lm_head_log_probs(hid, w, lab, temp, want_entropy=True)
+    lp, ent = st.fused_lm_head_log_probs(hid.to(dev), w.to(dev), lab.to(dev), temp, want_entropy=True)
+    assert float((lp.cpu() - want_lp).abs().max()) < TOL_LOGP
+    assert float((ent.cpu() - want_ent).abs().max()) < TOL_LOGP
+    assert bool((lp <= 0).all()) and bool((ent >= -1e-4).all()) and bool((ent <= math.log(v) + 1e-3).all())
+    lp2, none = st.fused_lm_head_log_probs(hid.to(dev), w.to(dev), lab.to(dev), temp)
+    assert none is None and torch.equal(lp2, lp)
+
+
+@pytest.mark.parametrize("rows,h,v,sigma,temp", HEAD_CASES[:3])
+def test_fused_log_probs_backward(st, dev, rows, h, v, sigma, temp):
+    hid, w = O.synth_head(rows, h, v, seed=rows + 1, sigma_w=sigma)
+    g = torch.Generator().manual_seed(rows)
+    lab = torch.randint(0, v, (rows,), generator=g)
+    gl = torch.randn(rows, generator=g) / rows
+    gl[::5] = 0.0  # masked tokens
+    ge = torch.randn(rows, generator=g) / rows
+    hf, wf = hid.float().requires_grad_(True), w.float().requires_grad_(True)
+    lp_ref, ent_ref = O.lm_head_log_probs(hf, wf, lab, temp, want_entropy=True)
+    ((lp_ref * gl).sum() + (ent_ref * ge).sum()).backward()
+    hd, wd = hid.to(dev).requires_grad_(True), w.to(dev).requires_grad_(True)
+    lp, ent = st.fused_lm_head_log_probs(hd, wd, lab.to(dev), temp, want_entropy=True)
+    ((lp * gl.to(dev)).sum() + (ent * ge.to(dev)).sum()).backward()
+    assert hd.grad.dtype == torch.bfloat16 and wd.grad.dtype == torch.bfloat16
+    assert rel(hd.grad, hf.grad) < TOL_REL
+    assert rel(wd.grad, wf.grad) < TOL_REL
+    assert float(hd.grad[::5].abs().max()) == 0.0 or rel(hd.grad[::5], hf.grad[::5]) < TOL_REL
+
+
+def test_fused_log_probs_multi_chunk_consistency(st, dev):
+    """More rows than one internal chunk (9472): results must not depend on where the chunk boundary falls."""
+    rows, h, v = 9472 + 700, 128, 4096
+    hid, w = O.synth_head(rows, h, v, seed=5, sigma_w=0.1)
+    lab = torch.randint(0, v, (rows,), generator=torch.Generator().manual_seed(5))
+    hd, wd, ld = hid.to(dev), w.to(dev), lab.to(dev)
+    whole, _ = st.fused_lm_head_log_probs(hd, wd, ld)
+    tail, _ = st.fused_lm_head_log_probs(hd[9000:], wd, ld[9000:])
+    assert torch.equal(whole[9000:], tail)  # bit-exact: same tiles, same order
+    want, _ = O.lm_head_log_probs(hid[9000:], w, lab[9000:])
+    assert float((tail.cpu() - want).abs().max()) < TOL_LOGP
+
+
+# ================================================================================================ fused GRPO loss
+def _loss_inputs(bsz, tl, h, v, n, sigma, seed, ragged=True):
+    hid, w = O.synth_head(bsz * tl, h, v, seed=seed, sigma_w=sigma)
+    hid = hid.view(bsz, tl, h)
+    roll = O.synth_rollout(bsz, tl, v, n, seed=seed, ragged=ragged)
+    logp, _ = O.lm_head_log_probs(hid, w, roll["responses"])
+    adv, _ = O.compute_grpo_outcome_advantage(roll["token_level_rewards"].clone(), roll["response_mask"], roll["uid"])
+    return {"hidden": hid, "weight": w, "labels": roll["responses"], "mask": roll["response_mask"], "adv": adv,
+            "old": O.perturbed_log_probs(logp, seed=seed + 1, outlier_frac=0.03),
+            "ref": O.perturbed_log_probs(logp, seed=seed + 2, outlier_frac=0.03), "roll": roll}
+
+
+def _check_fused_loss(st, dev, x, *, temperature=1.0, kl_penalty="low_var_kl", kl_coef=1e-2, grad_accum=4.0, use_ref=True,
+                      entropy_coeff=0.0):
+    want = O.fused_loss_reference(x["hidden"], x["weight"], x["labels"], x["old"], x["adv"], x["mask"],
+                                  x["ref"] if use_ref else None, temperature=temperature, kl_penalty=kl_penalty,
+                                  kl_coef=kl_coef, grad_accum=grad_accum, entropy_coef=entropy_coeff, want_entropy=True)
+    hd = x["hidden"].to(dev).requires_grad_(True)
+    wd = x["weight"].to(dev).requires_grad_(True)
+    loss, met = st.fused_grpo_loss(hd, wd, x["labels"].to(dev), x["old"].to(dev), x["adv"].to(dev),
+                                   x["ref"].to(dev) if use_ref else None, x["mask"].to(dev), temperature=temperature,
+                                   clip_ratio_low=CLIP[0], clip_ratio_high=CLIP[1], clip_ratio_dual=CLIP[2],
+                                   kl_penalty=kl_penalty, kl_coef=kl_coef, grad_accum=grad_accum,
+                                   entropy_coeff=entropy_coeff, want_entropy=True)
+    loss.backward()
+    wm = want["metrics"]
+    valid = x["mask"].bool()
+    assert float((met["log_probs"].cpu() - want["log_probs"])[valid].abs().max()) < TOL_LOGP
+    assert float((met["entropy"].cpu() - want["entropy"])[valid].abs().max()) < TOL_LOGP
+    assert abs(float(loss) - float(want["loss"])) <= TOL_REL * abs(float(want["loss"])) + 1e-7
+    for key in ("actor/pg_loss", "actor/entropy_loss", "actor/ppo_kl") + (("actor/kl_loss",) if use_ref else ()):
+        assert abs(float(met[key]) - float(wm[key])) <= TOL_REL * abs(float(wm[key])) + 1e-5, key
+    for key in ("actor/pg_clipfrac_higher", "actor/pg_clipfrac_lower"):
+        assert abs(float(met[key]) - float(wm[key])) <= 2e-3, key  # a token on a clip boundary may flip
+    assert rel(hd.grad, want["dhidden"]) < TOL_REL
+    assert rel(wd.grad, want["dweight"]) < TOL_REL
+    pad = ~valid
+    if pad.any():
+        assert float(hd.grad.cpu()[pad].abs().max()) == 0.0  # masked rows get exactly zero gradient
+    return want, met
+
+
+def test_fused_grpo_loss_golden(st, dev, golden):
+    g = golden("end_to_end")
+    for tag in ("flat", "peaked"):
+        hid = t(g[f"{tag}_hidden"]).to(torch.bfloat16)
+        w = t(g[f"{tag}_weight"]).to(torch.bfloat16)
+        uid = np.array([str(u) for u in g[f"{tag}_uid"]], dtype=object)
+        adv, _ = st.compute_grpo_outcome_advantage(t(g[f"{tag}_rewards"]).to(dev), t(g[f"{tag}_mask"]).to(dev), uid)
+        adv_close(adv, t(g[f"{tag}_adv"]))
+        hd, wd = hid.to(dev).requires_grad_(True), w.to(dev).requires_grad_(True)
+        loss, met = st.fused_grpo_loss(hd, wd, t(g[f"{tag}_labels"]).to(dev), t(g[f"{tag}_old"]).to(dev), adv,
+                                       t(g[f"{tag}_ref"]).to(dev), t(g[f"{tag}_mask"]).to(dev),
+                                       temperature=float(g[f"{tag}_temp"][0]), kl_penalty="low_var_kl", kl_coef=0.01,
+                                       grad_accum=2.0, want_entropy=True)
+        loss.backward()
+        sc = g[f"{tag}_scalars"]  # total, cf_hi, cf_lo, entropy_loss, ppo_kl, kl, pg
+        assert abs(float(loss) - sc[0] / 2.0) <= TOL_REL * abs(sc[0] / 2.0)
+        assert abs(float(met["actor/pg_loss"]) - sc[0]) <= TOL_REL * abs(sc[0])
+        assert abs(float(met["actor/pg_clipfrac_higher"]) - sc[1]) < 2e-2
+        assert abs(float(met["actor/entropy_loss"]) - sc[3]) <= TOL_REL * abs(sc[3])
+        assert abs(float(met["actor/kl_loss"]) - sc[5]) <= TOL_REL * abs(sc[5]) + 1e-6
+        valid = t(g[f"{tag}_mask"]).bool()
+        assert float((met["log_probs"].cpu() - t(g[f"{tag}_logp"]))[valid].abs().max()) < TOL_LOGP
+        assert float((met["entropy"].cpu() - t(g[f"{tag}_entropy"]))[valid].abs().max()) < TOL_LOGP
+        assert rel(hd.grad, t(g[f"{tag}_dhidden"])) < TOL_REL
+        assert rel(wd.grad, t(g[f"{tag}_dweight"])) < TOL_REL
+
+
+@pytest.mark.parametrize("sigma,temp", [(0.02, 1.0), (0.2, 0.8)])
+def test_fused_grpo_loss_vs_oracle(st, dev, sigma, temp):
+    x = _loss_inputs(8, 96, 256, 8192, 4, sigma, seed=31)
+    _check_fused_loss(st, dev, x, temperature=temp)
+
+
+@pytest.mark.parametrize("mode", ["kl", "abs", "mse", "chi2"])
+def test_fused_grpo_loss_kl_modes(st, dev, mode):
+    x = _loss_inputs(4, 40, 128, 2048, 4, 0.1, seed=41)
+    _check_fused_loss(st, dev, x, kl_penalty=mode, kl_coef=0.05)
+
+
+def test_fused_grpo_loss_no_ref_and_entropy_bonus(st, dev):
+    x = _loss_inputs(4, 64, 128, 4096, 4, 0.1, seed=51)
+    _check_fused_loss(st, dev, x, use_ref=False)
+    _check_fused_loss(st, dev, x, entropy_coeff=0.01)
+
+
+def test_fused_grpo_loss_edge_cases(st, dev):
+    x = _loss_inputs(4, 32, 128, 2048, 4, 0.1, seed=61)
+    hd, wd = x["hidden"].to(dev).requires_grad_(True), x["weight"].to(dev).requires_grad_(True)
+    zero = torch.zeros_like(x["mask"])
+    loss, met = st.fused_grpo_loss(hd, wd, x["labels"].to(dev), x["old"].to(dev), x["adv"].to(dev), None, zero.to(dev))
+    loss.backward()
+    assert float(loss) == 0.0 and float(hd.grad.abs().max()) == 0.0 and float(wd.grad.abs().max()) == 0.0  # KAT-D
+    # on-policy: old == current log-probs => ratio 1, no clipping, ppo_kl 0
+    lp, _ = st.fused_lm_head_log_probs(x["hidden"].to(dev), x["weight"].to(dev), x["labels"].to(dev))
+    loss, met = st.fused_grpo_loss(x["hidden"].to(dev), x["weight"].to(dev), x["labels"].to(dev), lp, x["adv"].to(dev),
+                                   None, x["mask"].to(dev))
+    assert float(met["actor/pg_clipfrac_higher"]) == 0 and float(met["actor/pg_clipfrac_lower"]) == 0
+    assert abs(float(met["actor/ppo_kl"])) < 1e-7
+    with pytest.raises(ValueError):
+        st.fused_grpo_loss(x["hidden"].float().to(dev), x["weight"].to(dev), x["labels"].to(dev), lp, x["adv"].to(dev),
+                           None, x["mask"].to(dev))
+    with pytest.raises(NotImplementedError):
+        st.fused_grpo_loss(x["hidden"].to(dev), x["weight"].to(dev), x["labels"].to(dev), lp, x["adv"].to(dev),
+                           x["ref"].to(dev), x["mask"].to(dev), kl_penalty="full", kl_coef=0.1)
+
+
+def test_config_c1_full_head(st, dev):
+    """BASELINE.json configs[0]: Qwen2.5-VL-3B head (H 2048, V 151936), 8 rollouts x 512 response tokens, against the
+    fp32 CPU oracle - log-probs, entropy, advantages, loss, dHidden, dW."""
+    x = _loss_inputs(8, 512, 2048, 151936, 8, 0.02, seed=71)
+    got_adv, _ = st.compute_grpo_outcome_advantage(x["roll"]["token_level_rewards"].to(dev), x["mask"].to(dev), x["roll"]["uid"])
+    adv_close(got_adv, x["adv"])
+    _check_fused_loss(st, dev, x, grad_accum=1.0)
+
+
+# ================================================================================================ actor loop
+def test_update_policy_matches_reference_loop(st, dev):
+    bsz, tl, h, v = 16, 48, 128, 4096
+    x = _loss_inputs(bsz, tl, h, v, 4, 0.1, seed=81)
+    batch = {"responses": x["labels"], "response_mask": x["mask"], "advantages": x["adv"], "old_log_probs": x["old"],
+             "ref_log_probs": x["ref"]}
+    want = O.update_policy_reference(x["hidden"], x["weight"], batch, global_batch_size_per_device=8,
+                                     micro_batch_size_per_device_for_update=2, temperature=0.9, kl_penalty="low_var_kl",
+                                     kl_coef=0.01)
+    cfg = st.ActorConfig(global_batch_size_per_device=8, micro_batch_size_per_device_for_update=2,
+                         micro_batch_size_per_device_for_experience=4, use_kl_loss=True, kl_penalty="low_var_kl", kl_coef=0.01)
+    actor = st.DataParallelPPOActor(cfg, x["weight"].to(dev))
+    tensors = {k: val.to(dev) for k, val in batch.items()}
+    tensors["hidden_states"] = x["hidden"].to(dev)
+    # the mask can also arrive as the tail of attention_mask, as in the reference (dp_actor.py:247)
+    data = st.TensorBatch(tensors, meta_info={"temperature": 0.9})
+    lp = actor.compute_log_prob(data)
+    want_lp, _ = O.lm_head_log_probs(x["hidden"], x["weight"], x["labels"], 0.9)
+    assert lp.shape == (bsz, tl) and float((lp.cpu() - want_lp).abs().max()) < TOL_LOGP
+    dws = []
+    orig_step = actor._optimizer_step
+
+    def spy():
+        dws.append(actor.dweight.clone())
+        return orig_step()
+
+    actor._optimizer_step = spy
+    met = actor.update_policy(data)
+    assert len(dws) == 2 and len(met["actor/pg_loss"]) == 8 and len(met["actor/grad_norm"]) == 2
+    assert isinstance(met["actor/kl_loss"], float) and met["actor/kl_coef"] == 0.01
+    for key in ("actor/pg_loss", "actor/entropy_loss", "actor/ppo_kl"):
+        np.testing.assert_allclose(met[key], want["metrics"][key], rtol=TOL_REL, atol=1e-5)
+    for i in range(2):
+        assert rel(dws[i], want["steps"][i]["dweight"]) < TOL_REL
+        gn = float(want["steps"][i]["dweight"].norm())
+        assert abs(met["actor/grad_norm"][i] - gn) <= TOL_REL * gn
+    got_dh = torch.cat([d for d in actor.last_dhidden], dim=0)
+    want_dh = want["steps"][0]["dhidden"] + want["steps"][1]["dhidden"]
+    assert rel(got_dh, want_dh) < TOL_REL
+    # attention_mask form of the mask
+    tensors2 = dict(tensors)
+    del tensors2["response_mask"]
+    tensors2["attention_mask"] = torch.cat([torch.ones(bsz, 5, dtype=torch.int64, device=dev), x["mask"].to(dev)], dim=1)
+    met2 = actor.update_policy(st.TensorBatch(tensors2, meta_info={"temperature": 0.9}))
+    np.testing.assert_allclose(met2["actor/pg_loss"], met["actor/pg_loss"], rtol=1e-6)
+
+
+def test_update_policy_with_hidden_fn_and_optimizer(st, dev):
+    """hidden_fn keeps an autograd graph: dHidden must reach the parameters behind it, and the optimizer must move W."""
+    bsz, tl, h, v = 8, 16, 64, 1024
+    x = _loss_inputs(bsz, tl, h, v, 4, 0.1, seed=91)
+    body = torch.nn.Linear(h, h, bias=False).to(dev).to(torch.bfloat16)
+    weight = torch.nn.Parameter(x["weight"].to(dev).clone())
+    opt = torch.optim.SGD([weight], lr=1.0)
+    cfg = st.ActorConfig(global_batch_size_per_device=8, micro_batch_size_per_device_for_update=4)
+    actor = st.DataParallelPPOActor(cfg, weight, actor_optimizer=opt, hidden_fn=lambda mb: body(mb["inputs"]))
+    data = st.TensorBatch({"inputs": x["hidden"].to(dev), "responses": x["labels"].to(dev), "response_mask": x["mask"].to(dev),
+                           "old_log_probs": x["old"].to(dev), "advantages": x["adv"].to(dev)}, meta_info={"temperature": 1.0})
+    before = weight.detach().clone()
+    met = actor.update_policy(data)
+    assert body.weight.grad is not None and float(body.weight.grad.abs().sum()) > 0
+    assert not torch.equal(before, weight.detach())
+    assert math.isfinite(met["actor/grad_norm"][0])
+
+
+# ================================================================================================ full-size properties
+def test_full_size_properties_7b_head(st, dev):
+    """BASELINE size (7B head, H 3584, V 151936) - too big for the CPU oracle in a test, so size-independent properties:
+    additivity of dW over row blocks, exact zeros for masked rows, log p <= 0, 0 <= entropy <= ln V, on-policy ratio."""
+    rows, h, v = 2 * 9472 + 1000, 3584, 151936  # three internal chunks, the last one ragged
+    g = torch.Generator().manual_seed(123)
+    hid = torch.randn(rows, h, generator=g).to(torch.bfloat16).to(dev)
+    w = (0.02 * torch.randn(v, h, generator=g)).to(torch.bfloat16).to(dev)
+    lab = torch.randint(0, v, (rows,), generator=g).to(dev)
+    mask = (torch.rand(rows, generator=g) > 0.3).long().to(dev)
+    adv = torch.randn(rows, generator=g).to(dev)
+    lp, ent = st.fused_lm_head_log_probs(hid, w, lab, 1.0, want_entropy=True)
+    assert bool((lp <= 0).all()) and bool((ent >= 0).all()) and bool((ent <= math.log(v) + 1e-3).all())
+    # spot-check 64 rows against torch on the device in fp32 (logits for 64 rows only)
+    idx = torch.randperm(rows, generator=g)[:64].to(dev)
+    z = hid[idx].float() @ w.float().t()
+    want = z.gather(1, lab[idx, None]).squeeze(1) - torch.logsumexp(z, -1)
+    assert float((lp[idx] - want).abs().max()) < TOL_LOGP
+    old = (lp + 0.05 * torch.randn(rows, generator=g).to(dev))
+    kw = dict(temperature=1.0, kl_penalty=None, grad_accum=2.0)
+    full = st.grpo_micro_batch_step(hid, w, lab, old, adv, None, mask, **kw)
+    assert float(full["dhidden"][mask == 0].abs().max()) == 0.0
+    # additivity: with the normaliser held fixed (same sum(mask) via grad_accum rescale), dW(all) = dW(A) + dW(B)
+    cut = 9472 + 333
+    m_all = float(mask.sum())
+    parts = torch.zeros_like(full["dweight"])
+    for sl in (slice(0, cut), slice(cut, rows)):
+        ga = 2.0 * m_all / float(mask[sl].sum())  # loss_part / ga == contribution of the part to loss_all / 2
+        st.grpo_micro_batch_step(hid[sl], w, lab[sl], old[sl], adv[sl], None, mask[sl], dweight_accum=parts,
+                                 temperature=1.0, kl_penalty=None, grad_accum=ga)
+    assert rel(parts, full["dweight"]) < 5e-3
+    # on-policy
+    on = st.grpo_micro_batch_step(hid, w, lab, lp, adv, None, mask, need_grads=False, **kw)
+    m = on["metrics"].cpu()
+    assert float(m[1]) == 0 and float(m[2]) == 0 and abs(float(m[3])) < 1e-7

@@ -1,0 +1,171 @@
+"""CPU-side checks: the C ABI library loads and exports everything the header declares, host-side index logic,
+containers, and the guarantee that the product never imports the oracle."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from spatialthinker_b200 import _lib, build
+
+    build.build(verbose=False)
+    return _lib.load()
+
+
+def test_header_symbols_exported(lib):
+    from spatialthinker_b200 import _lib
+
+    header = open(os.path.join(ROOT, "include", "grpo_b200.h")).read()
+    declared = set(re.findall(r"\b(grpo_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(raw, name), f"{name} declared in include/grpo_b200.h but not exported"
+    assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
+    assert lib.grpo_abi_version() == 1
+
+
+def test_workspace_queries_are_host_only(lib):
+    small = lib.grpo_lmhead_fwd_workspace_bytes(128, 2048, 151936)
+    big = lib.grpo_fused_loss_workspace_bytes(1 << 20, 3584, 151936)
+    assert 0 < small < big
+    # the stash never exceeds one chunk of rows, whatever the micro-batch size
+    assert big == lib.grpo_fused_loss_workspace_bytes(1 << 22, 3584, 151936)
+    assert big < 3.2e9
+
+
+def test_sass_is_blackwell_native():
+    from spatialthinker_b200 import _lib
+
+    try:
+        sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True, timeout=300).stdout
+    except FileNotFoundError:
+        pytest.skip("cuobjdump not available")
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):  # tcgen05.mma, TMA load, tcgen05.ld
+        assert mnemonic in sass, mnemonic
+    assert "HMMA." not in sass.replace("UTCHMMA", "")  # no legacy mma.sync path
+
+
+def test_product_fails_loudly_without_cuda_tensors():
+    import spatialthinker_b200 as st
+
+    z = torch.zeros(2, 8)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        st.log_probs_from_logits(z, torch.zeros(2, dtype=torch.int64))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        st.compute_kl(z, z, "kl")
+    with pytest.raises(NotImplementedError, match="Unknown KL penalty"):
+        st.compute_kl(z, z, "full")
+
+
+def test_missing_library_is_an_error(monkeypatch, tmp_path):
+    from spatialthinker_b200 import _lib
+
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_lib.GrpoLibraryError, match="no CPU or PyTorch fallback"):
+        _lib.load()
+
+
+def test_no_oracle_in_product():
+    pkg = os.path.join(ROOT, "spatialthinker_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), f
+                assert "grpo_oracle" not in text, f
+
+
+def test_group_csr():
+    from spatialthinker_b200.core_algos import group_csr
+
+    uid = np.array(["b", "a", "b", "c", "a", "c", "a"], dtype=object)
+    order, offsets = group_csr(uid)
+    groups = [sorted(order[offsets[i]:offsets[i + 1]].tolist()) for i in range(len(offsets) - 1)]
+    assert sorted(groups) == [[0, 2], [1, 4, 6], [3, 5]]
+    assert order.dtype == np.int32 and offsets.dtype == np.int32 and offsets[-1] == 7
+    with pytest.raises(AssertionError, match="rollout.n > 1"):
+        group_csr(np.array(["a", "a", "b"], dtype=object))
+    order, offsets = group_csr(torch.tensor([3, 3, 9, 9]))
+    assert offsets.tolist() == [0, 2, 4]
+
+
+def _reference_partitions():
+    """The reference's partitioner, executed from its source text (its module imports tensordict, which is absent)."""
+    path = "/root/reference/verl/utils/seqlen_balancing.py"
+    if not os.path.exists(path):
+        pytest.skip("reference checkout not present")
+    src = open(path).read()
+    src = src.replace("from tensordict import TensorDict", "TensorDict = object")
+    ns = {}
+    exec(compile(src, path, "exec"), ns)
+    return ns["get_seqlen_balanced_partitions"]
+
+
+@pytest.mark.parametrize("equal", [True, False])
+def test_balanced_partitions_match_reference(equal):
+    from spatialthinker_b200.sharding import balanced_partitions
+
+    ref = _reference_partitions()
+    rng = np.random.default_rng(0)
+    for n, k in ((64, 8), (32, 4), (128, 8), (16, 2), (24, 8)):
+        lens = rng.integers(1, 8192, size=n).tolist()
+        assert balanced_partitions(lens, k, equal) == ref(lens, k, equal)
+    lens = [5] * 16  # all ties
+    assert balanced_partitions(lens, 4, equal) == ref(lens, 4, equal)
+
+
+def test_balanced_partitions_properties():
+    from spatialthinker_b200.sharding import balanced_partitions, rank_rows
+
+    rng = np.random.default_rng(1)
+    lens = rng.integers(1, 4096, size=4096).tolist()
+    parts = balanced_partitions(lens, 8, True)
+    assert sorted(i for p in parts for i in p) == list(range(4096))
+    assert all(len(p) == 512 for p in parts)
+    sums = [sum(lens[i] for i in p) for p in parts]
+    assert max(sums) - min(sums) <= 0.001 * max(sums)
+    assert rank_rows(lens, 8, 3) == parts[3]
+    with pytest.raises(AssertionError):
+        balanced_partitions([1, 2, 3], 2, True)
+
+
+def test_tensor_batch_split_semantics():
+    from spatialthinker_b200.protocol import TensorBatch
+
+    tb = TensorBatch({"a": torch.arange(12).view(6, 2), "b": torch.arange(6)}, {"uid": np.arange(6)}, {"temperature": 0.7})
+    parts = tb.split(2)
+    assert len(parts) == 3 and parts[1].batch["b"].tolist() == [2, 3] and parts[2].non_tensor_batch["uid"].tolist() == [4, 5]
+    assert parts[0].meta_info["temperature"] == 0.7
+    assert list(tb.select(["b"]).batch) == ["b"]
+    with pytest.raises(AssertionError):
+        tb.chunk(4)
+    with pytest.raises(ValueError):
+        TensorBatch({"a": torch.zeros(3), "b": torch.zeros(4)})
+
+
+def test_patch_verl_roundtrip(reference_modules):
+    import spatialthinker_b200 as st
+
+    VF, ca = reference_modules
+    orig = ca.compute_policy_loss
+    done = st.patch_verl()
+    try:
+        assert "compute_policy_loss" in done["verl.trainer.core_algos"]
+        assert ca.compute_policy_loss is not orig and ca.compute_policy_loss.__wrapped__ is orig
+        if not torch.cuda.is_available():  # a GPU-less driver keeps running the reference's own code
+            out = ca.compute_kl(torch.zeros(3), torch.ones(3), "kl")
+            assert out.tolist() == [-1.0, -1.0, -1.0]
+    finally:
+        st.unpatch_verl()
+    assert ca.compute_policy_loss is orig
