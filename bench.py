@@ -1,0 +1,434 @@
+"""bench.py - GRPO loss fwd+bwd response-tokens/s on the Qwen2.5-VL-7B head shape (BASELINE.json metric / configs[2]).
+
+    python bench.py --gpus 1 --steps K --warmup W            # this library, one process per GPU (torchrun for N > 1)
+    python bench.py --impl reference --steps K --warmup W    # the reference arithmetic on the host cores (oracle port)
+
+One "step" = one pass of the hot path over one rollout batch: group-normalised advantages, then for every micro-batch
+lm_head -> log-probs -> clipped policy loss + low_var_kl -> dHidden and dW (accumulated in fp32), then per optimizer
+step the mean all-reduce of dW over ranks and its norm (dp_actor.py:155-167 minus the optimizer update itself, which is
+outside the path). The rollout batch of 512 prompts x n=8 x 1024 response tokens is sharded by sequence over the ranks
+(strong scaling: total work fixed).
+
+`value`  : tokens/s with every input already resident in HBM (CUDA events, max over ranks).
+`e2e`    : the same pass driven from PINNED HOST buffers through the public API: every micro-batch's inputs are copied
+           host->device inside the timed region (double-buffered on a copy stream) and the step's metrics are read back.
+`roofline`: the dominant kernel's algorithmic FLOP/s (2*H*V per row) over its CUDA-event duration, live, against the
+           measured bf16 tensor peak in MEASURED_PEAKS.json.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+CONFIGS = {
+    # name: (hidden, vocab, sequences, response_len, group n, description)
+    "c3": (3584, 151936, 4096, 1024, 8, "Qwen2.5-VL-7B head bf16, rollout batch 512 x n=8 x 1024 resp tokens, sequence-sharded"),
+    "c2": (2048, 151936, 1024, 1024, 8, "Qwen2.5-VL-3B head bf16, rollout batch 128 x n=8 x 1024 resp tokens"),
+    "c1": (2048, 151936, 8, 512, 8, "Qwen2.5-VL-3B head, 8 rollouts x 512 resp tokens"),
+    "c4": (3584, 151936, 4096, 2048, 8, "Qwen2.5-VL-7B head, ref low_var_kl + entropy output, 2048-token responses"),
+    "c5": (3584, 151936, 8192, 4096, 16, "Qwen2.5-VL-7B head, 4096 resp tokens, ragged masks, n=16"),
+}
+METRIC = "GRPO loss fwd+bwd response-tokens/s (7B head)"
+CLIP = dict(clip_ratio_low=0.2, clip_ratio_high=0.3, clip_ratio_dual=3.0)
+KL = dict(kl_penalty="low_var_kl", kl_coef=1e-2)
+OPT_STEPS = 4  # optimizer steps per rollout step: 4096 sequences / (global batch 128 x n 8), scripts/config.yaml:27
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"burst": p["bf16_tflops"], "sustained": p["bf16_tflops_sustained"], "hbm": p["hbm_gbs"], "src": "measured"}
+    return {"burst": 1590.0, "sustained": 1400.0, "hbm": 6650.0, "src": "fallback"}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi) for the timed region
+# ------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, pw, reasons = [], [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [s for s, p in zip(sm, pw) if p > 300] or sm
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# synthetic workload, generated per rank on the device
+# ------------------------------------------------------------------------------------------------------------------
+def make_inputs(cfg, rank, world, dev, micro_seqs, ragged):
+    hdim, vocab, bsz, tlen, n, _ = cfg
+    assert bsz % world == 0
+    local = bsz // world
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    gw = torch.Generator(device=dev).manual_seed(99)  # the weight is replicated: same seed on every rank
+    weight = torch.empty(vocab, hdim, dtype=torch.bfloat16, device=dev)
+    for r0 in range(0, vocab, 16384):
+        r1 = min(vocab, r0 + 16384)
+        weight[r0:r1] = (0.02 * torch.randn(r1 - r0, hdim, generator=gw, device=dev)).to(torch.bfloat16)
+    hidden = torch.empty(local, tlen, hdim, dtype=torch.bfloat16, device=dev)
+    for s0 in range(0, local, 8):
+        s1 = min(local, s0 + 8)
+        hidden[s0:s1] = torch.randn(s1 - s0, tlen, hdim, generator=g, device=dev).to(torch.bfloat16)
+    labels = torch.randint(0, vocab, (local, tlen), generator=g, device=dev)
+    if ragged:
+        lens = (1 + torch.floor(torch.rand(local, generator=g, device=dev) * tlen)).clamp(max=tlen).long()
+    else:
+        lens = torch.full((local,), tlen, dtype=torch.long, device=dev)
+    mask = (torch.arange(tlen, device=dev)[None, :] < lens[:, None]).long()
+    score = torch.rand(local, generator=g, device=dev)
+    rewards = torch.zeros(local, tlen, device=dev)
+    rewards[torch.arange(local, device=dev), lens - 1] = score
+    # uid: prompt id repeated n, rows permuted globally (groups straddle ranks), this rank's slice
+    gp = torch.Generator().manual_seed(7)
+    uid_all = torch.arange(bsz // n).repeat_interleave(n)[torch.randperm(bsz, generator=gp)]
+    # old / ref log-probs: a plausible level with jitter (their exact values do not change the work done)
+    old = -3.0 + 0.1 * torch.randn(local, tlen, generator=g, device=dev)
+    ref = -3.0 + 0.1 * torch.randn(local, tlen, generator=g, device=dev)
+    return {"weight": weight, "hidden": hidden, "labels": labels, "mask": mask, "rewards": rewards, "uid_np": uid_all.numpy(),
+            "old": old, "ref": ref, "local": local, "lens": lens}
+
+
+def step_plan(local, micro_seqs):
+    """(optimizer step, [micro-batch slices]) - mini-batches of local/OPT_STEPS sequences, micro-batches of micro_seqs."""
+    mini = max(local // OPT_STEPS, 1)
+    plan = []
+    for s0 in range(0, local, mini):
+        s1 = min(local, s0 + mini)
+        mbs = [slice(m0, min(m0 + micro_seqs, s1)) for m0 in range(s0, s1, micro_seqs)]
+        plan.append(mbs)
+    return plan
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# one step, device-resident inputs
+# ------------------------------------------------------------------------------------------------------------------
+def run_step_device(st, x, plan, dweight, world, temperature, want_entropy):
+    from spatialthinker_b200.sharding import allreduce_mean_
+
+    # advantages: groups straddle ranks, so the per-sequence scores are all-gathered (B floats) and the group statistics
+    # run redundantly per rank; this rank's rows are then broadcast over its response mask
+    rank = dist.get_rank() if world > 1 else 0
+    adv, _ = st.core_algos.compute_grpo_outcome_advantage_sharded(x["rewards"], x["mask"], x["uid_np"], rank * x["local"])
+    metrics, norms = [], []
+    for mbs in plan:
+        ga = float(len(mbs))
+        for sl in mbs:
+            res = st.grpo_micro_batch_step(x["hidden"][sl], x["weight"], x["labels"][sl], x["old"][sl], adv[sl], x["ref"][sl],
+                                           x["mask"][sl], temperature=temperature, grad_accum=ga, dweight_accum=dweight,
+                                           want_entropy=want_entropy, **CLIP, **KL)
+            metrics.append(res["metrics"])
+        allreduce_mean_(dweight)
+        norms.append(torch.linalg.vector_norm(dweight))
+        dweight.zero_()
+    return torch.stack(metrics), torch.stack(norms)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# one step, inputs in pinned host memory (end to end through the public API)
+# ------------------------------------------------------------------------------------------------------------------
+class HostFeed:
+    """Pinned host copies of this rank's inputs and two device staging sets; copies run on their own stream."""
+
+    KEYS = ("hidden", "labels", "old", "ref", "mask", "adv")
+
+    def __init__(self, x, adv, plan, dev):
+        self.dev = dev
+        self.host = {}
+        for k in self.KEYS:
+            src = adv if k == "adv" else x[k]
+            buf = torch.empty(src.shape, dtype=src.dtype, pin_memory=True)
+            buf.copy_(src)
+            self.host[k] = buf
+        self.max_mb = max(sl.stop - sl.start for mbs in plan for sl in mbs)
+        self.stage = [{k: torch.empty((self.max_mb,) + tuple(self.host[k].shape[1:]), dtype=self.host[k].dtype, device=dev)
+                       for k in self.KEYS} for _ in range(2)]
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.ready = [torch.cuda.Event(), torch.cuda.Event()]
+        self.free = [torch.cuda.Event(), torch.cuda.Event()]
+        self.bytes_per_step = sum(self.host[k][sl].numel() * self.host[k].element_size()
+                                  for mbs in plan for sl in mbs for k in self.KEYS)
+
+    def prefetch(self, slot, sl):
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.free[slot])
+            n = sl.stop - sl.start
+            for k in self.KEYS:
+                self.stage[slot][k][:n].copy_(self.host[k][sl], non_blocking=True)
+            self.ready[slot].record(self.copy_stream)
+
+    def get(self, slot, sl):
+        torch.cuda.current_stream(self.dev).wait_event(self.ready[slot])
+        n = sl.stop - sl.start
+        return {k: self.stage[slot][k][:n] for k in self.KEYS}
+
+    def release(self, slot):
+        self.free[slot].record(torch.cuda.current_stream(self.dev))
+
+
+def run_step_e2e(st, x, feed, plan, dweight, temperature, want_entropy, host_metrics):
+    from spatialthinker_b200.sharding import allreduce_mean_
+
+    flat = [(i, sl) for i, mbs in enumerate(plan) for sl in mbs]
+    feed.prefetch(0, flat[0][1])
+    metrics = []
+    for j, (i, sl) in enumerate(flat):
+        slot = j & 1
+        if j + 1 < len(flat):
+            feed.prefetch(slot ^ 1, flat[j + 1][1])
+        mb = feed.get(slot, sl)
+        res = st.grpo_micro_batch_step(mb["hidden"], x["weight"], mb["labels"], mb["old"], mb["adv"], mb["ref"], mb["mask"],
+                                       temperature=temperature, grad_accum=float(len(plan[i])), dweight_accum=dweight,
+                                       want_entropy=want_entropy, **CLIP, **KL)
+        feed.release(slot)
+        metrics.append(res["metrics"])
+        if j + 1 == len(flat) or flat[j + 1][0] != i:
+            allreduce_mean_(dweight)
+            metrics.append(torch.linalg.vector_norm(dweight).expand(metrics[0].shape[0]))
+            dweight.zero_()
+    host_metrics.copy_(torch.stack(metrics), non_blocking=True)  # the step's result goes back to the host
+    return host_metrics
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle (restatement of the reference arithmetic) on the host cores
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_pass(cfg, tokens, seed=0):
+    from oracle import grpo_oracle as O
+
+    hdim, vocab, _, _, n, _ = cfg
+    seqs = n
+    tlen = max(tokens // seqs, 1)
+    hid, w = O.synth_head(seqs * tlen, hdim, vocab, seed=seed)
+    hid = hid.view(seqs, tlen, hdim)
+    roll = O.synth_rollout(seqs, tlen, vocab, n, seed=seed)
+    old = -3.0 + 0.1 * torch.randn(seqs, tlen)
+    ref = -3.0 + 0.1 * torch.randn(seqs, tlen)
+    t0 = time.perf_counter()
+    adv, _ = O.compute_grpo_outcome_advantage(roll["token_level_rewards"].clone(), roll["response_mask"], roll["uid"])
+    O.fused_loss_reference(hid, w, roll["responses"], old, adv, roll["response_mask"], ref, kl_penalty="low_var_kl",
+                           kl_coef=1e-2, grad_accum=1.0)
+    return seqs * tlen, time.perf_counter() - t0
+
+
+def cpu_baseline(cfg, budget_s=15.0):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    tokens = 512
+    n_tok, dt = cpu_pass(cfg, tokens)  # also warms the thread pool
+    total_tok, total_t, passes = 0, 0.0, 0
+    while total_t < budget_s and passes < 8:
+        n_tok, dt = cpu_pass(cfg, tokens, seed=passes + 1)
+        total_tok += n_tok
+        total_t += dt
+        passes += 1
+    return {"value": total_tok / total_t, "unit": "tokens/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{passes} passes x {tokens} response tokens ({cfg[4]} sequences) of the same head shape, fp32 torch on "
+                      f"{cores} host threads; oracle/grpo_oracle.py (reference is pure Python, nothing to compile)"}
+
+
+def run_reference(args, cfg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    tokens = 512
+    for _ in range(max(args.warmup, 1)):
+        cpu_pass(cfg, tokens)
+    tot_tok, tot_t = 0, 0.0
+    for i in range(args.steps):
+        n_tok, dt = cpu_pass(cfg, tokens, seed=i)
+        tot_tok += n_tok
+        tot_t += dt
+    val = tot_tok / tot_t
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "tokens/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.config}: {cfg[5]}; each step = a bounded sample of {tokens} response tokens on the host"},
+        "cpu_baseline": {"value": val, "unit": "tokens/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"{args.steps} steps x {tokens} tokens, oracle port of the reference torch path"},
+        "e2e": {"value": val, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
+    ap.add_argument("--micro-seqs", type=int, default=0, help="sequences per micro-batch (0: 37888 tokens' worth)")
+    ap.add_argument("--sequences", type=int, default=0, help="override the rollout batch size (debug)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    cfg = list(CONFIGS[args.config])
+    if args.sequences:
+        cfg[2] = args.sequences
+    cfg = tuple(cfg)
+    if args.impl == "reference":
+        run_reference(args, cfg)
+        return
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import spatialthinker_b200 as st
+    from spatialthinker_b200 import _lib
+
+    lib = st.load_library()
+    hdim, vocab, bsz, tlen, n, desc = cfg
+    ragged = args.config == "c5"
+    want_entropy = args.config == "c4"
+    micro_seqs = args.micro_seqs or max(1, 37888 // tlen)  # 37 x 1024 tokens = 4 internal chunks of 9472 rows
+    x = make_inputs(cfg, rank, world, dev, micro_seqs, ragged)
+    plan = step_plan(x["local"], micro_seqs)
+    dweight = torch.zeros(vocab, hdim, dtype=torch.float32, device=dev)
+    tokens_local = int(x["mask"].sum().item())
+    tok = torch.tensor([tokens_local], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tok)
+    tokens_total = float(tok.item())
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        sync_all()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    dev_step = lambda: run_step_device(st, x, plan, dweight, world, 1.0, want_entropy)  # noqa: E731
+    for _ in range(args.warmup):
+        dev_step()
+    sampler = ClockSampler(local_rank)
+    launches0 = lib.grpo_launch_count()
+    lib.grpo_profile_enable(1)
+    lib.grpo_profile_read(None, None, 1)
+    if rank == 0:
+        sampler.start()
+    ms_total = timed(dev_step, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = lib.grpo_launch_count() - launches0
+    ph_ms = (ctypes.c_double * _lib.NUM_PHASES)()
+    ph_cnt = (ctypes.c_longlong * _lib.NUM_PHASES)()
+    lib.grpo_profile_read(ph_ms, ph_cnt, 1)
+    lib.grpo_profile_enable(0)
+    ms_per_step = ms_total / args.steps
+    value = tokens_total / (ms_per_step * 1e-3)
+
+    # ---- end to end from pinned host memory
+    e2e = None
+    if not args.no_e2e:
+        local_scores = x["rewards"].sum(-1)
+        adv = (local_scores - local_scores.mean())[:, None] * x["mask"]  # any advantage values: same work
+        feed = HostFeed(x, adv, plan, dev)
+        n_rows = sum(len(m) for m in plan) + len(plan)
+        host_metrics = torch.empty(n_rows, _lib.NUM_METRICS, dtype=torch.float32).pin_memory()
+        e2e_step = lambda: run_step_e2e(st, x, feed, plan, dweight, 1.0, want_entropy, host_metrics)  # noqa: E731
+        for _ in range(min(args.warmup, 1)):
+            e2e_step()
+        ms_e2e = timed(e2e_step, args.steps) / args.steps
+        e2e = {"value": tokens_total / (ms_e2e * 1e-3), "unit": "tokens/s", "h2d_bytes_per_step": int(feed.bytes_per_step * world),
+               "d2h_bytes_per_step": int(host_metrics.numel() * 4 * world), "ms_per_step": ms_e2e}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = load_peaks()
+    kernels = []
+    for i, name in enumerate(_lib.PHASE_NAMES):
+        if ph_cnt[i]:
+            kernels.append({"name": name, "launches": int(ph_cnt[i]), "avg_ms": ph_ms[i] / ph_cnt[i], "total_ms": ph_ms[i]})
+    gemms = [k for k in kernels if k["name"].endswith("_gemm")]
+    dom = max(gemms, key=lambda k: k["total_ms"])
+    rows_per_launch = tokens_local * args.steps / dom["launches"]  # every GEMM launch covers one chunk of rows
+    achieved = 2.0 * hdim * vocab * rows_per_launch / (dom["avg_ms"] * 1e-3) / 1e12
+    peak = peaks["sustained"]  # kernels are timed inside a seconds-long step under the power cap
+    roofline = {"bound": "tensor", "kernel": dom["name"], "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak, "peak_kind": f"{peaks['src']} sustained bf16 (burst {peaks['burst']})",
+                "traffic": None, "kernels": kernels,
+                "whole_step_tflops_algorithmic": 6.0 * hdim * vocab * tokens_total / (ms_per_step * 1e-3) / 1e12 / world}
+    out = {
+        "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": f"{args.config}: {desc}", "hidden": hdim, "vocab": vocab, "sequences": bsz, "response_len": tlen,
+                   "group_n": n, "micro_batch_sequences": micro_seqs, "optimizer_steps_per_step": len(plan),
+                   "loss": "GRPO clip .2/.3/3.0 + low_var_kl 1e-2", "l2": "inputs (>= 30 GB) far exceed the 126 MB L2",
+                   "parallelism": f"dp{world} by sequence, dW mean all-reduce (NCCL)"},
+        "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline, "e2e": e2e,
+    }
+    if not args.no_cpu:
+        out["cpu_baseline"] = cpu_baseline(cfg)
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

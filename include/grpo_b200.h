@@ -54,6 +54,16 @@ typedef struct CUstream_st* grpo_stream_t;
 int grpo_abi_version(void);
 const char* grpo_last_error(void);
 
+/* Measurement evidence (bench.py): number of this library's kernels enqueued so far by the process, and optional
+ * CUDA-event timing of the pipeline phases on the caller's stream.
+ *   phases: 0 logits GEMM (+softmax statistics), 1 row combine, 2 token loss, 3 stash -> dlogits transform,
+ *           4 dHidden GEMM, 5 dW GEMM.   grpo_profile_read synchronises on the recorded events (call it outside the
+ *           timed region); ms_out / count_out are [GRPO_NUM_PHASES] totals since the last reset. */
+#define GRPO_NUM_PHASES 6
+long long grpo_launch_count(void);
+int grpo_profile_enable(int on);
+int grpo_profile_read(double* ms_out, long long* count_out, int reset);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * lm_head -> token log-prob / entropy, forward only.
  * Replaces: HF `self.lm_head(hidden_states)` reached from dp_actor.py:118-125, `logits.div_(temperature)` :126 and
@@ -128,6 +138,16 @@ int grpo_masked_mean(const float* x, const void* mask, int mask_dtype, int64_t n
 int grpo_advantage(const float* rewards, const void* mask, int mask_dtype, const int32_t* order,
                    const int32_t* offsets, int64_t bsz, int64_t t_len, int64_t n_groups, float eps, float* advantages,
                    float* seq_scratch, grpo_stream_t stream);
+
+/* The same in two steps, for a batch sharded by sequence over ranks (groups straddle ranks after the trainer's
+ * sequence balancing, ray_trainer.py:628): each rank scores its own rows, the scores are all-gathered (bsz_all floats),
+ * every rank runs the group statistics and broadcasts its rows [row_begin, row_begin + bsz_local) over its mask.
+ *   seq_scratch f32 [bsz_all] device scratch (normalised score of every sequence). */
+int grpo_sequence_scores(const float* rewards, int64_t bsz, int64_t t_len, float* scores, grpo_stream_t stream);
+int grpo_advantage_from_scores(const float* scores_all, const int32_t* order, const int32_t* offsets, int64_t bsz_all,
+                               int64_t n_groups, float eps, int64_t row_begin, const void* mask, int mask_dtype,
+                               int64_t bsz_local, int64_t t_len, float* advantages, float* seq_scratch,
+                               grpo_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * log_probs_from_logits on MATERIALISED logits (torch_functional.py:45-66), API parity only.

@@ -18,6 +18,8 @@ KL_MODES = {None: -1, "none": -1, "low_var_kl": 0, "kl": 1, "abs": 2, "mse": 3, 
 MASK_F32, MASK_I64, MASK_U8, MASK_NONE = 0, 1, 2, 3
 LOGITS_F32, LOGITS_BF16, LOGITS_F16 = 0, 1, 2
 NUM_METRICS = 10
+NUM_PHASES = 6
+PHASE_NAMES = ("logits_gemm", "combine", "token_loss", "stash_to_dlogits", "dhidden_gemm", "dweight_gemm")
 MET_PG_LOSS, MET_CLIPFRAC_HI, MET_CLIPFRAC_LO, MET_PPO_KL, MET_KL_LOSS = 0, 1, 2, 3, 4
 MET_ENTROPY, MET_TOTAL, MET_SCALED, MET_TRUE_ENTROPY, MET_MASK_SUM = 5, 6, 7, 8, 9
 
@@ -25,6 +27,9 @@ _P = c_void_p
 _SIGNATURES = {
     "grpo_abi_version": (c_int, []),
     "grpo_last_error": (c_char_p, []),
+    "grpo_launch_count": (ctypes.c_longlong, []),
+    "grpo_profile_enable": (c_int, [c_int]),
+    "grpo_profile_read": (c_int, [_P, _P, c_int]),
     "grpo_lmhead_fwd_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "grpo_lmhead_logprob_fwd": (c_int, [_P, _P, _P, c_int64, c_int64, c_int64, c_float, _P, _P, _P, _P, c_size_t, _P]),
     "grpo_lmhead_bwd_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
@@ -42,6 +47,8 @@ _SIGNATURES = {
     "grpo_compute_kl": (c_int, [_P, _P, c_int64, c_int, _P, _P, _P]),
     "grpo_masked_mean": (c_int, [_P, _P, c_int, c_int64, c_float, _P, _P, _P]),
     "grpo_advantage": (c_int, [_P, _P, c_int, _P, _P, c_int64, c_int64, c_int64, c_float, _P, _P, _P]),
+    "grpo_sequence_scores": (c_int, [_P, c_int64, c_int64, _P, _P]),
+    "grpo_advantage_from_scores": (c_int, [_P, _P, _P, c_int64, c_int64, c_float, c_int64, _P, c_int, c_int64, c_int64, _P, _P, _P]),
     "grpo_logprob_from_logits": (c_int, [_P, c_int, _P, c_int64, c_int64, c_int64, _P, _P, _P, _P]),
     "grpo_logprob_from_logits_bwd": (c_int, [_P, c_int, _P, _P, _P, _P, _P, c_int64, c_int64, c_int64, _P, c_int64, _P]),
     "grpo_debug_gemm": (c_int, [_P, _P, _P, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_int, _P]),

@@ -79,6 +79,51 @@ def compute_grpo_outcome_advantage(
     return adv, adv
 
 
+@torch.no_grad()
+def compute_grpo_outcome_advantage_sharded(
+    token_level_rewards: torch.Tensor,
+    response_mask: torch.Tensor,
+    index_all: Sequence,
+    row_begin: int,
+    eps: float = 1e-6,
+    group=None,
+) -> Tuple[torch.Tensor, torch.Tensor]:
+    """The same advantages when the batch is sharded by sequence over data-parallel ranks.
+
+    ``token_level_rewards`` / ``response_mask`` are this rank's rows ``[row_begin, row_begin + bs_local)`` of the global
+    batch (equal row counts per rank, rank order = row order); ``index_all`` is the uid of EVERY sequence. Scores are
+    all-gathered (``bs_all`` floats over NCCL), the group statistics run redundantly on every rank.
+    """
+    from .sharding import all_gather_rows
+
+    dev = require_cuda(token_level_rewards, response_mask)
+    bsz, t_len = token_level_rewards.shape
+    order, offsets = group_csr(index_all)
+    lib = _lib.load()
+    rewards = f32c(token_level_rewards)
+    mask, code = mask_arg(response_mask)
+    scores = torch.empty(bsz, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.grpo_sequence_scores(rewards.data_ptr(), bsz, t_len, scores.data_ptr(), _lib.stream_ptr(dev)),
+                   "grpo_sequence_scores")
+    scores_all = all_gather_rows(scores, group)
+    bsz_all = scores_all.shape[0]
+    if bsz_all != len(index_all):
+        raise ValueError(f"index_all has {len(index_all)} entries but the gathered batch has {bsz_all} sequences")
+    order_d = torch.from_numpy(order).to(dev, non_blocking=True)
+    offsets_d = torch.from_numpy(offsets).to(dev, non_blocking=True)
+    adv = torch.empty(bsz, t_len, dtype=torch.float32, device=dev)
+    seq = torch.empty(max(bsz_all, 1), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(
+            lib.grpo_advantage_from_scores(scores_all.data_ptr(), order_d.data_ptr(), offsets_d.data_ptr(), bsz_all,
+                                           offsets.size - 1, float(eps), int(row_begin), mask.data_ptr(), code, bsz,
+                                           t_len, adv.data_ptr(), seq.data_ptr(), _lib.stream_ptr(dev)),
+            "grpo_advantage_from_scores",
+        )
+    return adv, adv
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # policy loss
 # ----------------------------------------------------------------------------------------------------------------

@@ -32,7 +32,31 @@ struct TileSched {
   uint32_t k_blocks;  // K blocks of 64
   uint32_t panel_m;   // row blocks per panel
   uint32_t m_fast;
+  // Optional lock-step: every `sync_period` K-blocks of progress all CTA groups meet at a global counter, so tiles that
+  // share an operand panel read it from L2 while it is still resident (persistent CTAs otherwise drift apart, every
+  // group then streams its own copy from HBM, and the extra DRAM traffic costs SM clock under the power cap).
+  uint32_t sync_period;  // in K-blocks; 0 = free running
+  uint32_t* sync_ctr;    // zeroed by the host before the launch
 };
+
+// Arrive at round `round` (1-based) of the progress barrier and wait for all `groups` producers. A producer that waits
+// too long stops waiting for the rest of the kernel (it still arrives, so nobody else can hang on it).
+__device__ __forceinline__ void progress_sync(uint32_t* ctr, uint32_t round, uint32_t groups, bool& give_up) {
+  atomicAdd(ctr, 1u);
+  if (give_up) return;
+  const uint32_t target = round * groups;
+  const long long t0 = clock64();
+  while (true) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+    if (v >= target) break;
+    if (clock64() - t0 > 400000) {  // ~0.25 ms: someone is not co-resident; run free from here on
+      give_up = true;
+      break;
+    }
+    __nanosleep(64);
+  }
+}
 
 __device__ __forceinline__ void decode_tile(const TileSched& s, uint32_t t, uint32_t& m_blk, uint32_t& n_blk) {
   const uint32_t per_panel = s.panel_m * s.n_blocks;
@@ -125,12 +149,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
+      const bool do_sync = leader && sched.sync_period != 0 && sched.sync_ctr != nullptr;
+      uint32_t progress = 0, rounds_done = 0;
+      bool give_up = false;
       for (uint32_t t = first_tile; t < num_tiles; t += tile_step) {
         uint32_t m_blk, n_blk;
         decode_tile(sched, t, m_blk, n_blk);
         const int32_t m0 = static_cast<int32_t>(m_blk * (kBlockM * kCta) + rank * kBlockM);
         const int32_t n0 = static_cast<int32_t>(n_blk * BLOCK_N + rank * Cfg::kLoadN);
-        for (uint32_t kb = 0; kb < sched.k_blocks; ++kb) {
+        for (uint32_t kb = 0; kb < sched.k_blocks; ++kb, ++progress) {
+          if (do_sync && progress != 0 && progress % sched.sync_period == 0)
+            progress_sync(sched.sync_ctr, ++rounds_done, tile_step, give_up);
           mbar_wait(&empty_bar[stage], phase ^ 1);
           const int32_t k0 = static_cast<int32_t>(kb * kBlockK);
           uint8_t* sa = smem_a + stage * Cfg::kABytes;
@@ -153,6 +182,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           else mbar_arrive_cluster(&full_bar[stage], 0);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
+      }
+      if (do_sync) {  // groups with fewer tiles keep arriving so the others never wait on them
+        const uint32_t max_tiles = (num_tiles + tile_step - 1) / tile_step;
+        const uint32_t total = max_tiles * sched.k_blocks;
+        const uint32_t rounds = total == 0 ? 0 : (total - 1) / sched.sync_period;
+        for (; rounds_done < rounds; ++rounds_done) atomicAdd(sched.sync_ctr, 1u);
       }
     }
   } else if (warp == 1) {

@@ -6,7 +6,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <mutex>
+#include <utility>
+#include <vector>
 
 #include "advantage_kernels.cuh"
 #include "gemm_core.cuh"
@@ -35,6 +38,53 @@ static int fail(int code, const char* fmt, ...) {
     int rc__ = (expr);        \
     if (rc__ != 0) return rc__; \
   } while (0)
+
+// ------------------------------------------------------------------------------------------ launch counter / phase timer
+// Evidence plumbing for bench.py: how many of OUR kernels were enqueued, and (when enabled) CUDA-event timing of each
+// pipeline phase on the caller's stream. Disabled by default; costs nothing then.
+static std::atomic<long long> g_launches{0};
+static inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+enum Phase { PH_LOGITS_GEMM = 0, PH_COMBINE, PH_LOSS, PH_TRANSFORM, PH_DH_GEMM, PH_DW_GEMM, PH_N };
+struct Profiler {
+  std::atomic<bool> on{false};
+  std::mutex mu;
+  std::vector<cudaEvent_t> pool;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending[PH_N];
+  double ms[PH_N] = {};
+  long long cnt[PH_N] = {};
+  cudaEvent_t get() {
+    if (!pool.empty()) {
+      cudaEvent_t e = pool.back();
+      pool.pop_back();
+      return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+  }
+};
+static Profiler g_prof;
+struct PhaseScope {
+  Phase ph;
+  cudaStream_t st;
+  cudaEvent_t e0 = nullptr;
+  PhaseScope(Phase p, cudaStream_t s) : ph(p), st(s) {
+    if (g_prof.on.load(std::memory_order_relaxed)) {
+      std::lock_guard<std::mutex> lk(g_prof.mu);
+      e0 = g_prof.get();
+      cudaEventRecord(e0, st);
+    }
+  }
+  ~PhaseScope() {
+    if (e0) {
+      std::lock_guard<std::mutex> lk(g_prof.mu);
+      cudaEvent_t e1 = g_prof.get();
+      cudaEventRecord(e1, st);
+      g_prof.pending[ph].push_back({e0, e1});
+    }
+  }
+};
 
 // ------------------------------------------------------------------------------------------ TMA descriptors
 using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -83,7 +133,19 @@ static int make_operand_tmap(CUtensorMap* map, const void* base, uint64_t rows, 
 struct DevInfo {
   int sms = 0;
   int cta_group = 2;
+  // tuning knobs (environment overrides are for experiments; the defaults are what is measured in profiles/)
+  int fwd_panel = 19;   // row blocks of the logits GEMM kept L2-resident under the vocab sweep (19 x 256 x H bf16)
+  // progress-barrier periods in K-blocks (0 = off). Measured on B200 (profiles/r1_knobs.md): the barrier does bound
+  // the drift between CTA pairs but the chunk pipeline is power-capped, and the stalls it adds cost as much as the
+  // DRAM traffic it saves - so the default is free-running.
+  int sync_fwd = 0;
+  int sync_dh = 0;
+  int sync_dw = 0;
 };
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return (e && *e) ? atoi(e) : dflt;
+}
 static int get_dev(DevInfo* out) {
   static DevInfo cached[64];
   static bool have[64] = {};
@@ -97,6 +159,10 @@ static int get_dev(DevInfo* out) {
     cached[dev].sms = p.multiProcessorCount;
     const char* e = getenv("GRPO_CTA_GROUP");
     cached[dev].cta_group = (e && e[0] == '1') ? 1 : 2;
+    cached[dev].fwd_panel = env_int("GRPO_FWD_PANEL", cached[dev].fwd_panel);
+    cached[dev].sync_fwd = env_int("GRPO_SYNC_FWD", cached[dev].sync_fwd);
+    cached[dev].sync_dh = env_int("GRPO_SYNC_DH", cached[dev].sync_dh);
+    cached[dev].sync_dw = env_int("GRPO_SYNC_DW", cached[dev].sync_dw);
     have[dev] = true;
   }
   *out = cached[dev];
@@ -128,6 +194,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const TileS
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   GRPO_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, sched, ep));
+  count_launch();
   return 0;
 }
 
@@ -166,6 +233,7 @@ struct Workspace {
   float *part_max = nullptr, *part_sum = nullptr, *part_ez = nullptr;
   float *target_z = nullptr, *lse = nullptr, *dlogp = nullptr, *dent = nullptr, *ent = nullptr;
   double* acc = nullptr;
+  uint32_t* sync = nullptr;  // progress-barrier counters, one per GEMM of the chunk pipeline
   size_t bytes = 0;
 };
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -195,6 +263,7 @@ static Workspace carve(void* base, int64_t rows, int64_t vocab, bool with_stash)
   w.dent = reinterpret_cast<float*>(take(vec));
   w.ent = reinterpret_cast<float*>(take(vec));
   w.acc = reinterpret_cast<double*>(take(ACC_N * sizeof(double)));
+  w.sync = reinterpret_cast<uint32_t*>(take(64));
   w.bytes = off;
   return w;
 }
@@ -232,14 +301,23 @@ static int chunk_forward(const DevInfo& dev, const Workspace& w, const __nv_bflo
   static_assert(sizeof(p1) == sizeof(p2), "epilogue params layout");
   GRPO_CUDA(cudaMemsetAsync(w.target_z, 0, static_cast<size_t>(n) * 4, stream));
   TileSched s{};
-  s.m_fast = 1;  // walk all row blocks of the chunk under one vocab tile: hidden chunk stays in L2, W streams once
-  GRPO_TRY((launch_gemm_any<false, false, EpiSoftmax<1, kBlockN>, EpiSoftmax<2, kBlockN>>(
-      dev.cta_group, hidden + r0 * h, n, h, weight, v, h, h, s, p1, p2, dev.sms, stream)));
+  s.m_fast = 1;  // walk the row blocks of a panel under one vocab tile: the hidden panel stays in L2, W streams by
+  s.panel_m = static_cast<uint32_t>(dev.fwd_panel * (dev.cta_group == 1 ? 2 : 1));  // counted in blocks of 128 * cta_group
+  s.sync_period = static_cast<uint32_t>(dev.sync_fwd);
+  s.sync_ctr = w.sync;
+  GRPO_CUDA(cudaMemsetAsync(w.sync, 0, 64, stream));
+  {
+    PhaseScope ps(PH_LOGITS_GEMM, stream);
+    GRPO_TRY((launch_gemm_any<false, false, EpiSoftmax<1, kBlockN>, EpiSoftmax<2, kBlockN>>(
+        dev.cta_group, hidden + r0 * h, n, h, weight, v, h, h, s, p1, p2, dev.sms, stream)));
+  }
+  PhaseScope ps(PH_COMBINE, stream);
   const uint32_t threads = 128;
   combine_rows_kernel<<<cdiv(n, threads), threads, 0, stream>>>(
       w.part_max, w.part_sum, want_entropy ? w.part_ez : nullptr, w.target_z, labels + r0, static_cast<uint32_t>(n),
       static_cast<uint32_t>(w.rows_pad), static_cast<uint32_t>(w.n_tiles), static_cast<uint32_t>(v), lse_out,
       logp_out, ent_out);
+  count_launch();
   GRPO_CUDA(cudaGetLastError());
   return 0;
 }
@@ -250,25 +328,33 @@ static int chunk_backward(const DevInfo& dev, const Workspace& w, const __nv_bfl
                           const float* ent, const float* lse, int64_t r0, int64_t n, int64_t h, int64_t v,
                           float temperature, __nv_bfloat16* dhidden, float* dweight, cudaStream_t stream) {
   {
+    PhaseScope ps(PH_TRANSFORM, stream);
     dim3 grid(cdiv(v / 8, 256 * 4), static_cast<uint32_t>(n < 65535 ? n : 65535));
     stash_to_dlogits_kernel<kBlockN><<<grid, 256, 0, stream>>>(
         w.stash, v, static_cast<uint32_t>(n), static_cast<uint32_t>(v), w.part_max, static_cast<uint32_t>(w.rows_pad),
         lse, dlogp, dent, ent, labels + r0, 1.f / temperature);
+    count_launch();
     GRPO_CUDA(cudaGetLastError());
   }
   {  // dHidden[n][h] = G[n][v] . W[v][h]       A = G (K-major), B = W read "transposed" (MN-major)
+    PhaseScope ps(PH_DH_GEMM, stream);
     EpiBF16<1, kBlockN>::Params p1{dhidden + r0 * h, h, static_cast<uint32_t>(n), static_cast<uint32_t>(h)};
     EpiBF16<2, kBlockN>::Params p2{dhidden + r0 * h, h, static_cast<uint32_t>(n), static_cast<uint32_t>(h)};
     TileSched s{};
     s.m_fast = 0;  // all H column blocks of a few row blocks run together: W streams once per wave
+    s.sync_period = static_cast<uint32_t>(dev.sync_dh);
+    s.sync_ctr = w.sync + 1;
     GRPO_TRY((launch_gemm_any<false, true, EpiBF16<1, kBlockN>, EpiBF16<2, kBlockN>>(
         dev.cta_group, w.stash, n, v, weight, h, h, v, s, p1, p2, dev.sms, stream)));
   }
   {  // dW[v][h] += G^T[v][n] . hidden[n][h]    A = G read transposed (MN-major), B = hidden read transposed
+    PhaseScope ps(PH_DW_GEMM, stream);
     EpiF32<1, kBlockN>::Params p1{dweight, h, static_cast<uint32_t>(v), static_cast<uint32_t>(h), 1u};
     EpiF32<2, kBlockN>::Params p2{dweight, h, static_cast<uint32_t>(v), static_cast<uint32_t>(h), 1u};
     TileSched s{};
     s.m_fast = 0;  // the H column blocks of one vocab block run together: the G panel is read from HBM once
+    s.sync_period = static_cast<uint32_t>(dev.sync_dw);
+    s.sync_ctr = w.sync + 2;
     GRPO_TRY((launch_gemm_any<true, true, EpiF32<1, kBlockN>, EpiF32<2, kBlockN>>(
         dev.cta_group, w.stash, v, v, hidden + r0 * h, h, h, n, s, p1, p2, dev.sms, stream)));
   }
@@ -301,6 +387,34 @@ extern "C" {
 
 int grpo_abi_version(void) { return 1; }
 const char* grpo_last_error(void) { return g_err; }
+long long grpo_launch_count(void) { return g_launches.load(); }
+
+int grpo_profile_enable(int on) {
+  g_prof.on.store(on != 0);
+  return 0;
+}
+int grpo_profile_read(double* ms_out, long long* count_out, int reset) {
+  std::lock_guard<std::mutex> lk(g_prof.mu);
+  for (int p = 0; p < PH_N; ++p) {
+    for (auto& pr : g_prof.pending[p]) {
+      GRPO_CUDA(cudaEventSynchronize(pr.second));
+      float ms = 0.f;
+      GRPO_CUDA(cudaEventElapsedTime(&ms, pr.first, pr.second));
+      g_prof.ms[p] += ms;
+      g_prof.cnt[p] += 1;
+      g_prof.pool.push_back(pr.first);
+      g_prof.pool.push_back(pr.second);
+    }
+    g_prof.pending[p].clear();
+    if (ms_out) ms_out[p] = g_prof.ms[p];
+    if (count_out) count_out[p] = g_prof.cnt[p];
+    if (reset) {
+      g_prof.ms[p] = 0.0;
+      g_prof.cnt[p] = 0;
+    }
+  }
+  return 0;
+}
 
 size_t grpo_lmhead_fwd_workspace_bytes(int64_t rows, int64_t, int64_t vocab) {
   return carve(nullptr, rows, vocab, false).bytes;
@@ -315,9 +429,9 @@ size_t grpo_fused_loss_workspace_bytes(int64_t rows, int64_t, int64_t vocab) {
 int grpo_lmhead_logprob_fwd(const void* hidden, const void* weight, const int64_t* labels, int64_t rows,
                             int64_t hidden_dim, int64_t vocab, float temperature, float* logp, float* entropy,
                             float* lse, void* workspace, size_t workspace_bytes, grpo_stream_t stream) {
+  if (rows == 0) return 0;
   GRPO_TRY(check_head_args(hidden, weight, rows, hidden_dim, vocab, temperature));
   if (!labels || !logp) return fail(GRPO_ERR_ARG, "labels / logp must not be null");
-  if (rows == 0) return 0;
   DevInfo dev;
   GRPO_TRY(get_dev(&dev));
   const Workspace w = carve(workspace, rows, vocab, false);
@@ -336,10 +450,10 @@ int grpo_lmhead_logprob_fwd(const void* hidden, const void* weight, const int64_
 int grpo_lmhead_bwd(const void* hidden, const void* weight, const int64_t* labels, const float* dlogp,
                     const float* dentropy, int64_t rows, int64_t hidden_dim, int64_t vocab, float temperature,
                     void* dhidden, float* dweight, void* workspace, size_t workspace_bytes, grpo_stream_t stream) {
+  if (rows == 0) return 0;
   GRPO_TRY(check_head_args(hidden, weight, rows, hidden_dim, vocab, temperature));
   if (!labels || !dlogp || !dhidden || !dweight)
     return fail(GRPO_ERR_ARG, "labels / dlogp / dhidden / dweight must not be null");
-  if (rows == 0) return 0;
   DevInfo dev;
   GRPO_TRY(get_dev(&dev));
   const Workspace w = carve(workspace, rows, vocab, true);
@@ -392,6 +506,7 @@ int grpo_fused_loss_fwd_bwd(const void* hidden, const void* weight, const int64_
     // the normaliser sum(mask) spans the whole micro-batch and is needed before the first dL/dlogp (dp_actor.py:255)
     mask_sum_kernel<<<ew_blocks(rows, 256, dev.sms), 256, 0, stream>>>(mask, mask_dtype, static_cast<size_t>(rows),
                                                                         w.acc);
+    count_launch();
     GRPO_CUDA(cudaGetLastError());
   }
   const bool want_ent = entropy_out != nullptr;
@@ -400,10 +515,14 @@ int grpo_fused_loss_fwd_bwd(const void* hidden, const void* weight, const int64_
     GRPO_TRY(chunk_forward(dev, w, hp, wp, labels, r0, n, hidden_dim, vocab, temperature, want_ent, want_bwd,
                            logp_out + r0, want_ent ? entropy_out + r0 : nullptr, w.lse, stream));
     const void* mchunk = (mask_dtype == MASK_NONE) ? nullptr : static_cast<const uint8_t*>(mask) + r0 * esz;
-    token_loss_kernel<<<ew_blocks(n, 256, dev.sms), 256, 0, stream>>>(
+    {
+      PhaseScope ps(PH_LOSS, stream);
+      token_loss_kernel<<<ew_blocks(n, 256, dev.sms), 256, 0, stream>>>(
         logp_out + r0, old_logp + r0, advantages + r0, ref_logp ? ref_logp + r0 : nullptr,
         want_ent ? entropy_out + r0 : nullptr, mchunk, mask_dtype, static_cast<size_t>(n), cfg, w.acc,
         want_bwd ? w.dlogp : nullptr, (want_bwd && entropy_coef != 0.f) ? w.dent : nullptr);
+      count_launch();
+    }
     GRPO_CUDA(cudaGetLastError());
     if (want_bwd)
       GRPO_TRY(chunk_backward(dev, w, hp, wp, labels, w.dlogp, entropy_coef != 0.f ? w.dent : nullptr,
@@ -411,6 +530,7 @@ int grpo_fused_loss_fwd_bwd(const void* hidden, const void* weight, const int64_
                               static_cast<__nv_bfloat16*>(dhidden), dweight, stream));
   }
   loss_finalize_kernel<<<1, 32, 0, stream>>>(w.acc, cfg, metrics);
+  count_launch();
   GRPO_CUDA(cudaGetLastError());
   return 0;
 }
@@ -433,10 +553,13 @@ int grpo_policy_loss_fwd_bwd(const float* logp, const float* old_logp, const flo
   if (n > 0) {
     const uint32_t blocks = ew_blocks(n, 256, 0);
     mask_sum_kernel<<<blocks, 256, 0, stream>>>(mask, mask_dtype, static_cast<size_t>(n), acc_scratch);
+    count_launch();
     token_loss_kernel<<<blocks, 256, 0, stream>>>(logp, old_logp, advantages, ref_logp, nullptr, mask, mask_dtype,
                                                   static_cast<size_t>(n), cfg, acc_scratch, dlogp, nullptr);
+    count_launch();
   }
   loss_finalize_kernel<<<1, 32, 0, stream>>>(acc_scratch, cfg, metrics);
+  count_launch();
   GRPO_CUDA(cudaGetLastError());
   return 0;
 }
@@ -448,6 +571,7 @@ int grpo_compute_kl(const float* logp, const float* ref_logp, int64_t n, int kl_
   if (n <= 0) return n == 0 ? 0 : fail(GRPO_ERR_ARG, "negative length");
   kl_elementwise_kernel<<<ew_blocks(n, 256, 0), 256, 0, stream>>>(logp, ref_logp, static_cast<size_t>(n), kl_mode, out,
                                                                   dout_dlogp);
+  count_launch();
   GRPO_CUDA(cudaGetLastError());
   return 0;
 }
@@ -462,7 +586,45 @@ int grpo_masked_mean(const float* x, const void* mask, int mask_dtype, int64_t n
   if (n > 0)
     masked_sum_kernel<<<ew_blocks(n, 256, 0), 256, 0, stream>>>(x, mask, mask_dtype, static_cast<size_t>(n),
                                                                 acc_scratch);
+    count_launch();
   masked_mean_finalize_kernel<<<1, 32, 0, stream>>>(acc_scratch, eps, out);
+  count_launch();
+  GRPO_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int grpo_sequence_scores(const float* rewards, int64_t bsz, int64_t t_len, float* scores, grpo_stream_t stream) {
+  if (bsz == 0) return 0;
+  if (!rewards || !scores) return fail(GRPO_ERR_ARG, "rewards / scores must not be null");
+  if (bsz < 0 || t_len <= 0 || bsz > 0x7fffffffll || t_len > 0x7fffffffll) return fail(GRPO_ERR_ARG, "bad dimensions");
+  row_score_kernel<<<cdiv(bsz * 32, 256), 256, 0, stream>>>(rewards, static_cast<uint32_t>(bsz),
+                                                            static_cast<uint32_t>(t_len), scores);
+  count_launch();
+  GRPO_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int grpo_advantage_from_scores(const float* scores_all, const int32_t* order, const int32_t* offsets, int64_t bsz_all,
+                               int64_t n_groups, float eps, int64_t row_begin, const void* mask, int mask_dtype,
+                               int64_t bsz_local, int64_t t_len, float* advantages, float* seq_scratch,
+                               grpo_stream_t stream) {
+  if (!scores_all || !order || !offsets || !advantages || !seq_scratch)
+    return fail(GRPO_ERR_ARG, "scores_all / order / offsets / advantages / seq_scratch must not be null");
+  if (mask_dtype < 0 || mask_dtype > 3 || (mask_dtype != MASK_NONE && !mask))
+    return fail(GRPO_ERR_ARG, "bad mask / mask_dtype");
+  if (bsz_all < 0 || n_groups < 0 || row_begin < 0 || bsz_local < 0 || row_begin + bsz_local > bsz_all || t_len < 0 ||
+      bsz_all > 0x7fffffffll || t_len > 0x7fffffffll)
+    return fail(GRPO_ERR_ARG, "bad dimensions");
+  if (bsz_all == 0) return 0;
+  group_stats_kernel<<<cdiv(n_groups * 32, 256), 256, 0, stream>>>(scores_all, order, offsets,
+                                                                   static_cast<uint32_t>(n_groups), eps, seq_scratch);
+  count_launch();
+  if (bsz_local > 0 && t_len > 0) {
+    broadcast_adv_kernel<<<ew_blocks(bsz_local * t_len, 256, 0), 256, 0, stream>>>(
+        seq_scratch + row_begin, mask, mask_dtype, static_cast<uint32_t>(bsz_local), static_cast<uint32_t>(t_len),
+        advantages);
+    count_launch();
+  }
   GRPO_CUDA(cudaGetLastError());
   return 0;
 }
@@ -481,34 +643,40 @@ int grpo_advantage(const float* rewards, const void* mask, int mask_dtype, const
   float* seq_adv = seq_scratch + bsz;
   const uint32_t b = static_cast<uint32_t>(bsz), t = static_cast<uint32_t>(t_len);
   row_score_kernel<<<cdiv(bsz * 32, 256), 256, 0, stream>>>(rewards, b, t, scores);
+  count_launch();
   group_stats_kernel<<<cdiv(n_groups * 32, 256), 256, 0, stream>>>(scores, order, offsets,
                                                                    static_cast<uint32_t>(n_groups), eps, seq_adv);
+  count_launch();
   broadcast_adv_kernel<<<ew_blocks(bsz * t_len, 256, 0), 256, 0, stream>>>(seq_adv, mask, mask_dtype, b, t,
                                                                            advantages);
+  count_launch();
   GRPO_CUDA(cudaGetLastError());
   return 0;
 }
 
 int grpo_logprob_from_logits(const void* logits, int logits_dtype, const int64_t* labels, int64_t rows, int64_t vocab,
                              int64_t ld, float* logp, float* entropy, float* lse, grpo_stream_t stream) {
+  if (rows == 0) return 0;
   if (!logits || (logp && !labels)) return fail(GRPO_ERR_ARG, "logits (and labels when logp is wanted) must not be null");
   if (rows < 0 || vocab <= 0 || ld < vocab || rows > 0x7fffffffll || vocab > 0x7fffffffll)
     return fail(GRPO_ERR_ARG, "bad dimensions");
-  if (rows == 0) return 0;
   const uint32_t r = static_cast<uint32_t>(rows), v = static_cast<uint32_t>(vocab);
   const int threads = vocab >= 8192 ? 512 : 128;
   switch (logits_dtype) {
     case LOGITS_F32:
       logprob_from_logits_kernel<float><<<r, threads, 0, stream>>>(static_cast<const float*>(logits), labels, r, v, ld,
                                                                    logp, entropy, lse);
+      count_launch();
       break;
     case LOGITS_BF16:
       logprob_from_logits_kernel<__nv_bfloat16><<<r, threads, 0, stream>>>(
           static_cast<const __nv_bfloat16*>(logits), labels, r, v, ld, logp, entropy, lse);
+      count_launch();
       break;
     case LOGITS_F16:
       logprob_from_logits_kernel<__half><<<r, threads, 0, stream>>>(static_cast<const __half*>(logits), labels, r, v,
                                                                     ld, logp, entropy, lse);
+      count_launch();
       break;
     default: return fail(GRPO_ERR_ARG, "unknown logits dtype %d", logits_dtype);
   }
@@ -519,6 +687,7 @@ int grpo_logprob_from_logits(const void* logits, int logits_dtype, const int64_t
 int grpo_logprob_from_logits_bwd(const void* logits, int logits_dtype, const int64_t* labels, const float* lse,
                                  const float* dlogp, const float* dentropy, const float* entropy, int64_t rows,
                                  int64_t vocab, int64_t ld, void* dlogits, int64_t ld_out, grpo_stream_t stream) {
+  if (rows == 0) return 0;
   if (!logits || !lse || !dlogits) return fail(GRPO_ERR_ARG, "logits / lse / dlogits must not be null");
   if (dlogp && !labels) return fail(GRPO_ERR_ARG, "dlogp needs labels");
   if (dentropy && !entropy) return fail(GRPO_ERR_ARG, "dentropy needs the forward entropy");
@@ -532,16 +701,19 @@ int grpo_logprob_from_logits_bwd(const void* logits, int logits_dtype, const int
       logprob_from_logits_bwd_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(logits), labels, lse,
                                                                       dlogp, dentropy, entropy, r, v, ld,
                                                                       static_cast<float*>(dlogits), ld_out);
+      count_launch();
       break;
     case LOGITS_BF16:
       logprob_from_logits_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(
           static_cast<const __nv_bfloat16*>(logits), labels, lse, dlogp, dentropy, entropy, r, v, ld,
           static_cast<__nv_bfloat16*>(dlogits), ld_out);
+      count_launch();
       break;
     case LOGITS_F16:
       logprob_from_logits_bwd_kernel<__half><<<grid, 256, 0, stream>>>(static_cast<const __half*>(logits), labels, lse,
                                                                        dlogp, dentropy, entropy, r, v, ld,
                                                                        static_cast<__half*>(dlogits), ld_out);
+      count_launch();
       break;
     default: return fail(GRPO_ERR_ARG, "unknown logits dtype %d", logits_dtype);
   }

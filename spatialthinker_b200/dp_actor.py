@@ -126,6 +126,8 @@ class DataParallelPPOActor:
         temperature = _get(data, "meta_info")["temperature"]
         keys = ["responses"] + [k for k in ("hidden_states", "input_ids", "attention_mask", "position_ids")
                                 if k in _get(data, "batch")]
+        if self.hidden_fn is not None:  # whatever the body needs travels with the micro-batch
+            keys = list(_get(data, "batch").keys())
         outs = []
         for mb in data.select(keys).split(self.config.micro_batch_size_per_device_for_experience):
             micro = {**mb.batch, **mb.non_tensor_batch}
@@ -144,6 +146,8 @@ class DataParallelPPOActor:
                  if k in _get(data, "batch")]
         if use_ref:
             keys.append("ref_log_probs")
+        if self.hidden_fn is not None:
+            keys += [k for k in _get(data, "batch").keys() if k not in keys and k != "ref_log_probs"]
         mini_batches = data.select(keys).split(cfg.global_batch_size_per_device)
 
         if self.dweight is None:

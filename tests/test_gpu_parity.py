@@ -201,6 +201,11 @@ def test_advantage_full_size_vs_oracle(st, dev):
     with pytest.raises(AssertionError):
         st.compute_grpo_outcome_advantage(torch.ones(3, 2, device=dev), torch.ones(3, 2, device=dev),
                                           np.array(["a", "a", "b"], dtype=object))
+    # the sharded entry (scores -> all-gather -> statistics -> local broadcast) with a single rank is the same function
+    got, ret = st.core_algos.compute_grpo_outcome_advantage_sharded(roll["token_level_rewards"].to(dev),
+                                                                    roll["response_mask"].to(dev), roll["uid"], 0)
+    assert got is ret
+    adv_close(got, want)
 
 
 # ================================================================================================ fused lm_head
