@@ -409,9 +409,15 @@ def main():
     rows_per_launch = tokens_local * args.steps / dom["launches"]  # every GEMM launch covers one chunk of rows
     achieved = 2.0 * hdim * vocab * rows_per_launch / (dom["avg_ms"] * 1e-3) / 1e12
     peak = peaks["sustained"]  # kernels are timed inside a seconds-long step under the power cap
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath) and (hdim, vocab) == (3584, 151936):  # the ncu capture was taken at this head shape
+        t = json.load(open(tpath)).get(dom["name"])
+        if t:
+            traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
     roofline = {"bound": "tensor", "kernel": dom["name"], "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak, "peak_kind": f"{peaks['src']} sustained bf16 (burst {peaks['burst']})",
-                "traffic": None, "kernels": kernels,
+                "traffic": traffic, "algorithmic_flops_per_launch": 2.0 * hdim * vocab * rows_per_launch, "kernels": kernels,
                 "whole_step_tflops_algorithmic": 6.0 * hdim * vocab * tokens_total / (ms_per_step * 1e-3) / 1e12 / world}
     out = {
         "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
