@@ -56,11 +56,14 @@ const char* grpo_last_error(void);
 
 /* Measurement evidence (bench.py): number of this library's kernels enqueued so far by the process, and optional
  * CUDA-event timing of the pipeline phases on the caller's stream.
- *   phases: 0 logits GEMM (+softmax statistics), 1 row combine, 2 token loss, 3 stash -> dlogits transform,
- *           4 dHidden GEMM, 5 dW GEMM.   grpo_profile_read synchronises on the recorded events (call it outside the
+ *   phases: 0 logits GEMM (+softmax sums, exp stash), 1 row statistics (label logit + combine), 2 token loss,
+ *           3 gradient preparation (row scales + one-hot scatter, or stash -> dlogits), 4 dHidden GEMM, 5 dW GEMM.   grpo_profile_read synchronises on the recorded events (call it outside the
  *           timed region); ms_out / count_out are [GRPO_NUM_PHASES] totals since the last reset. */
 #define GRPO_NUM_PHASES 6
 long long grpo_launch_count(void);
+/* Tuning knobs for experiments (process-wide): "cta_group" 1|2, "fwd_panel" row blocks, "sync_fwd" / "sync_dh" /
+ * "sync_dw" progress-barrier periods in K-blocks (0 = off), "l2_hints" 0|1. Defaults are the measured configuration. */
+int grpo_set_option(const char* name, int value);
 int grpo_profile_enable(int on);
 int grpo_profile_read(double* ms_out, long long* count_out, int reset);
 

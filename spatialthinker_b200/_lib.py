@@ -19,7 +19,7 @@ MASK_F32, MASK_I64, MASK_U8, MASK_NONE = 0, 1, 2, 3
 LOGITS_F32, LOGITS_BF16, LOGITS_F16 = 0, 1, 2
 NUM_METRICS = 10
 NUM_PHASES = 6
-PHASE_NAMES = ("logits_gemm", "combine", "token_loss", "stash_to_dlogits", "dhidden_gemm", "dweight_gemm")
+PHASE_NAMES = ("logits_gemm", "row_stats", "token_loss", "grad_prep", "dhidden_gemm", "dweight_gemm")
 MET_PG_LOSS, MET_CLIPFRAC_HI, MET_CLIPFRAC_LO, MET_PPO_KL, MET_KL_LOSS = 0, 1, 2, 3, 4
 MET_ENTROPY, MET_TOTAL, MET_SCALED, MET_TRUE_ENTROPY, MET_MASK_SUM = 5, 6, 7, 8, 9
 
@@ -28,6 +28,7 @@ _SIGNATURES = {
     "grpo_abi_version": (c_int, []),
     "grpo_last_error": (c_char_p, []),
     "grpo_launch_count": (ctypes.c_longlong, []),
+    "grpo_set_option": (c_int, [c_char_p, c_int]),
     "grpo_profile_enable": (c_int, [c_int]),
     "grpo_profile_read": (c_int, [_P, _P, c_int]),
     "grpo_lmhead_fwd_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),

@@ -10,7 +10,9 @@
 //
 // Operand majorness is a template parameter: K-major operands are [rows][K] row-major in global memory, MN-major
 // operands are [K][rows] row-major (the "transposed" reads the backward GEMMs need) - both are fed by plain 2-D TMA
-// boxes in 128-byte-swizzle layout, so no transposed copies are ever materialised in HBM.
+// boxes in 128-byte-swizzle layout, so no transposed copies are ever materialised in HBM. The A operand can also live
+// in a BLOCKED layout [blk][blk][64][64] (8 KB contiguous per 64 x 64 block): one 4-D TMA box then fetches the same
+// smem image as the 2-D boxes would, from contiguous HBM, whichever of the two dimensions the GEMM treats as K.
 #pragma once
 #include "ptx.cuh"
 
@@ -22,6 +24,14 @@ constexpr int kUmmaK = 16;
 constexpr int kNumThreads = 256;
 constexpr int kEpiWarp0 = 4;
 constexpr int kNumEpiThreads = 128;
+
+// A-operand storage / majorness (bit 0 = MN-major for the MMA descriptor)
+enum AMode : int {
+  A_K_MAJOR = 0,     // [rows][K] row-major
+  A_MN_MAJOR = 1,    // [K][rows] row-major
+  A_BLOCKED_K = 2,   // [rows/64][K/64][64 rows][64 k]   : K-major tile image
+  A_BLOCKED_MN = 3,  // [K/64][rows/64][64 k][64 rows]   : MN-major tile image (the same buffer, other dimension as K)
+};
 
 // Tile walk: tiles are grouped in panels of `panel_m` row-blocks; inside a panel either the row-block index (m_fast)
 // or the column-block index runs fastest. Chosen per GEMM so that the operand re-read by neighbouring CTAs is the
@@ -37,14 +47,18 @@ struct TileSched {
   // group then streams its own copy from HBM, and the extra DRAM traffic costs SM clock under the power cap).
   uint32_t sync_period;  // in K-blocks; 0 = free running
   uint32_t* sync_ctr;    // zeroed by the host before the launch
+  // L2 eviction priority of the two operand streams (kEvictNormal / kEvictFirst / kEvictLast)
+  uint64_t hint_a, hint_b;
 };
 
-// Arrive at round `round` (1-based) of the progress barrier and wait for all `groups` producers. A producer that waits
-// too long stops waiting for the rest of the kernel (it still arrives, so nobody else can hang on it).
+// Progress window `round` (1-based) starts: announce it, then make sure every one of the `groups` producers has at least
+// STARTED the previous window. That bounds the skew between CTA groups to two windows without ever stalling a producer
+// that is merely level with the others (a full barrier here costs ~10 % of tensor-pipe time, measured). A producer that
+// waits too long stops waiting for the rest of the kernel (it still announces, so nobody can hang on it).
 __device__ __forceinline__ void progress_sync(uint32_t* ctr, uint32_t round, uint32_t groups, bool& give_up) {
   atomicAdd(ctr, 1u);
-  if (give_up) return;
-  const uint32_t target = round * groups;
+  if (give_up || round < 2) return;
+  const uint32_t target = (round - 1) * groups;
   const long long t0 = clock64();
   while (true) {
     uint32_t v;
@@ -82,7 +96,7 @@ struct EpiCtx {
   uint32_t tmem_acc;     // TMEM address of this warp's lanes, column 0 of the accumulator stage
 };
 
-template <int kCta, int BLOCK_N, int kStages, bool kAMn, bool kBMn>
+template <int kCta, int BLOCK_N, int kStages>
 struct GemmCfg {
   static constexpr int kLoadN = BLOCK_N / kCta;  // B columns each CTA loads
   static constexpr int kABytes = kBlockM * kBlockK * 2;
@@ -96,11 +110,12 @@ struct GemmCfg {
   static constexpr size_t smem_bytes(int epi_bytes) { return 1024 + kRingBytes + epi_bytes + kBarBytes; }
 };
 
-template <int kCta, int BLOCK_N, int kStages, bool kAMn, bool kBMn, class Epi>
+template <int kCta, int BLOCK_N, int kStages, int kAMode, bool kBMn, class Epi>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
             const TileSched sched, const typename Epi::Params ep) {
-  using Cfg = GemmCfg<kCta, BLOCK_N, kStages, kAMn, kBMn>;
+  using Cfg = GemmCfg<kCta, BLOCK_N, kStages>;
+  constexpr bool kAMn = (kAMode & 1) != 0;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
@@ -164,19 +179,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           const int32_t k0 = static_cast<int32_t>(kb * kBlockK);
           uint8_t* sa = smem_a + stage * Cfg::kABytes;
           uint8_t* sb = smem_b + stage * Cfg::kBBytes;
-          if constexpr (!kAMn) {
-            tma_load_2d<kCta>(&tmap_a, &full_bar[stage], sa, k0, m0);
-          } else {
+          if constexpr (kAMode == A_K_MAJOR) {
+            tma_load_2d<kCta>(&tmap_a, &full_bar[stage], sa, k0, m0, sched.hint_a);
+          } else if constexpr (kAMode == A_MN_MAJOR) {
 #pragma unroll
             for (int i = 0; i < kBlockM / 64; ++i)
-              tma_load_2d<kCta>(&tmap_a, &full_bar[stage], sa + i * (kBlockK * 128), m0 + i * 64, k0);
+              tma_load_2d<kCta>(&tmap_a, &full_bar[stage], sa + i * (kBlockK * 128), m0 + i * 64, k0, sched.hint_a);
+          } else if constexpr (kAMode == A_BLOCKED_K) {  // box (64, 64, 1 K-block, 2 row blocks)
+            tma_load_4d<kCta>(&tmap_a, &full_bar[stage], sa, 0, 0, static_cast<int32_t>(kb), m0 >> 6, sched.hint_a);
+          } else {  // A_BLOCKED_MN: box (64, 64, 2 row blocks, 1 K-block)
+            tma_load_4d<kCta>(&tmap_a, &full_bar[stage], sa, 0, 0, m0 >> 6, static_cast<int32_t>(kb), sched.hint_a);
           }
           if constexpr (!kBMn) {
-            tma_load_2d<kCta>(&tmap_b, &full_bar[stage], sb, k0, n0);
+            tma_load_2d<kCta>(&tmap_b, &full_bar[stage], sb, k0, n0, sched.hint_b);
           } else {
 #pragma unroll
             for (int i = 0; i < Cfg::kLoadN / 64; ++i)
-              tma_load_2d<kCta>(&tmap_b, &full_bar[stage], sb + i * (kBlockK * 128), n0 + i * 64, k0);
+              tma_load_2d<kCta>(&tmap_b, &full_bar[stage], sb + i * (kBlockK * 128), n0 + i * 64, k0, sched.hint_b);
           }
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes * kCta);
           else mbar_arrive_cluster(&full_bar[stage], 0);
@@ -290,34 +309,57 @@ struct EpiF32 {
   }
 };
 
-// bf16 result, plain store into C[M][ldc].
+// bf16 result into C[M][ldc]:  C[r][:] = row_scale[r] * acc[r][:] + onehot[r] * gather[idx[r]][:]
+// (row_scale == nullptr: 1; onehot == nullptr: no gather term). The gather term is how the dHidden GEMM adds the
+// one-hot part of dL/dlogits, (g_r / T) * W[label_r][:], without it ever being written into the stash.
 template <int kCta, int BLOCK_N>
 struct EpiBF16 {
   struct Params {
     __nv_bfloat16* c;
     int64_t ldc;
     uint32_t m, n;
+    const float* row_scale;          // [m] or nullptr
+    const float* onehot;             // [m] or nullptr
+    const int64_t* idx;              // [m] row of `gather` to add (ignored where onehot[r] == 0)
+    const __nv_bfloat16* gather;     // [*][ld_gather]
+    int64_t ld_gather;
   };
   static constexpr int kSmemBytes = 0;
   __device__ static void run(const Params& p, const EpiCtx& c, uint8_t*) {
     const uint32_t row = c.m_blk * (kBlockM * kCta) + c.row_in_tile;
     const uint32_t col0 = c.n_blk * BLOCK_N;
+    const bool row_ok = row < p.m;
     __nv_bfloat16* out = p.c + static_cast<int64_t>(row) * p.ldc + col0;
+    const float sc = (row_ok && p.row_scale) ? p.row_scale[row] : 1.f;
+    const float oh = (row_ok && p.onehot) ? p.onehot[row] : 0.f;
+    const __nv_bfloat16* grow = (oh != 0.f) ? p.gather + p.idx[row] * p.ld_gather + col0 : nullptr;
 #pragma unroll 1
     for (int g = 0; g < BLOCK_N / 32; ++g) {
       uint32_t v[32];
       tmem_ld_32x32(c.tmem_acc + g * 32, v);
       tmem_ld_wait();
-      if (row < p.m) {
+      if (row_ok) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const uint32_t col = col0 + g * 32 + q * 8;
           if (col < p.n) {  // n % 8 == 0
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[8 * q + i]) * sc;
+            if (grow) {
+              const uint4 w = *reinterpret_cast<const uint4*>(grow + g * 32 + q * 8);
+              const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                f[2 * i] = fmaf(oh, __uint_as_float(ww[i] << 16), f[2 * i]);
+                f[2 * i + 1] = fmaf(oh, __uint_as_float(ww[i] & 0xffff0000u), f[2 * i + 1]);
+              }
+            }
             uint4 pk;
-            pk.x = pack_bf16x2(__uint_as_float(v[8 * q + 0]), __uint_as_float(v[8 * q + 1]));
-            pk.y = pack_bf16x2(__uint_as_float(v[8 * q + 2]), __uint_as_float(v[8 * q + 3]));
-            pk.z = pack_bf16x2(__uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5]));
-            pk.w = pack_bf16x2(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7]));
+            pk.x = pack_bf16x2(f[0], f[1]);
+            pk.y = pack_bf16x2(f[2], f[3]);
+            pk.z = pack_bf16x2(f[4], f[5]);
+            pk.w = pack_bf16x2(f[6], f[7]);
             *reinterpret_cast<uint4*>(out + g * 32 + q * 8) = pk;
           }
         }

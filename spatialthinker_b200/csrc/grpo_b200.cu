@@ -45,7 +45,7 @@ static int fail(int code, const char* fmt, ...) {
 static std::atomic<long long> g_launches{0};
 static inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
-enum Phase { PH_LOGITS_GEMM = 0, PH_COMBINE, PH_LOSS, PH_TRANSFORM, PH_DH_GEMM, PH_DW_GEMM, PH_N };
+enum Phase { PH_LOGITS_GEMM = 0, PH_ROW_STATS, PH_LOSS, PH_GRAD_PREP, PH_DH_GEMM, PH_DW_GEMM, PH_N };
 struct Profiler {
   std::atomic<bool> on{false};
   std::mutex mu;
@@ -87,6 +87,7 @@ struct PhaseScope {
 };
 
 // ------------------------------------------------------------------------------------------ TMA descriptors
+static inline uint64_t cdiv64(uint64_t x) { return (x + 63) / 64; }
 using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -122,59 +123,98 @@ static int make_tmap_bf16(CUtensorMap* map, const void* base, uint64_t inner, ui
   return 0;
 }
 
-// operand [rows][k] (K-major) or [k][rows] (MN-major) -> descriptor with the box the producer warp expects
-static int make_operand_tmap(CUtensorMap* map, const void* base, uint64_t rows, uint64_t k, uint64_t pitch_elems,
-                             bool mn_major, uint32_t rows_per_load) {
-  if (!mn_major) return make_tmap_bf16(map, base, k, rows, pitch_elems, kBlockK, rows_per_load);
-  return make_tmap_bf16(map, base, rows, k, pitch_elems, 64, kBlockK);
+// Blocked bf16 operand [blk3][blk2][64][64] (64 x 64 blocks of 8 KB, inner row = 128 B); box = (64, 64, box2, box3).
+static int make_tmap_blocked(CUtensorMap* map, const void* base, uint64_t n_blk2, uint64_t n_blk3, uint64_t blk3_pitch,
+                             uint32_t box2, uint32_t box3) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(GRPO_ERR_DRIVER, "cuTensorMapEncodeTiled entry point not available");
+  if (reinterpret_cast<uintptr_t>(base) & 15u) return fail(GRPO_ERR_ARG, "TMA operand must be 16-byte aligned");
+  const cuuint64_t dims[4] = {64, 64, n_blk2, n_blk3};
+  const cuuint64_t strides[3] = {128, 8192, blk3_pitch * 8192};
+  const cuuint32_t box[4] = {64, 64, box2, box3};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(GRPO_ERR_DRIVER, "cuTensorMapEncodeTiled (blocked) failed with CUresult %d", (int)r);
+  return 0;
 }
 
-// ------------------------------------------------------------------------------------------ device info
-struct DevInfo {
-  int sms = 0;
-  int cta_group = 2;
-  // tuning knobs (environment overrides are for experiments; the defaults are what is measured in profiles/)
-  int fwd_panel = 19;   // row blocks of the logits GEMM kept L2-resident under the vocab sweep (19 x 256 x H bf16)
-  // progress-barrier periods in K-blocks (0 = off). Measured on B200 (profiles/r1_knobs.md): the barrier does bound
-  // the drift between CTA pairs but the chunk pipeline is power-capped, and the stalls it adds cost as much as the
-  // DRAM traffic it saves - so the default is free-running.
-  int sync_fwd = 0;
-  int sync_dh = 0;
-  int sync_dw = 0;
+// A/B operand descriptor with the box the producer warp expects.
+//   plain : [rows][k] (K-major) or [k][rows] (MN-major), row pitch `pitch` elements
+//   blocked (A only): 64 x 64 blocks; `pitch` = number of blocks along the buffer's inner block dimension
+static int make_operand_tmap(CUtensorMap* map, const void* base, uint64_t rows, uint64_t k, uint64_t pitch, int mode,
+                             uint32_t rows_per_load) {
+  switch (mode) {
+    case A_K_MAJOR: return make_tmap_bf16(map, base, k, rows, pitch, kBlockK, rows_per_load);
+    case A_MN_MAJOR: return make_tmap_bf16(map, base, rows, k, pitch, 64, kBlockK);
+    case A_BLOCKED_K:  // [rows/64][k/64][64][64]: blk2 = K blocks, blk3 = row blocks
+      return make_tmap_blocked(map, base, cdiv64(k), cdiv64(rows), pitch, 1, rows_per_load / 64);
+    default:           // A_BLOCKED_MN: [k/64][rows/64][64][64]: blk2 = row blocks, blk3 = K blocks
+      return make_tmap_blocked(map, base, cdiv64(rows), cdiv64(k), pitch, rows_per_load / 64, 1);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ device info / knobs
+// Tuning knobs. Defaults are what profiles/ measures; GRPO_* environment variables (read once) or grpo_set_option()
+// override them for experiments.
+struct Knobs {
+  int cta_group = 2;   // 2: one 256 x 256 tile per CTA pair (cta_group::2); 1: 128 x 256 per CTA (debug)
+  int fwd_panel = 19;  // row blocks (of 256) of the logits GEMM kept L2-resident under the vocab sweep (19 x 256 x H bf16)
+  // progress-barrier periods in K-blocks (0 = off). Measured on B200 (profiles/r1_knobs.md): the barrier cuts DRAM
+  // traffic but its stalls cost more tensor-pipe time than the traffic costs clock - default free-running.
+  int sync_fwd = 0, sync_dh = 0, sync_dw = 0;
+  // L2 eviction priorities on the TMA loads, bit 0: logits GEMM (hidden panel evict-last, W evict-first), bit 1: dW GEMM
+  // (scaled hidden evict-last, stash evict-first). Measured (profiles/r1_knobs.md): both cost 2-3 % - default off.
+  int l2_hints = 0;
+  int dh_m_fast = 0;   // tile order of the dHidden GEMM (experiment)
+  int chunk_rows = 9472;  // rows per chunk of the pipeline (multiple of 256)
 };
+static Knobs g_knobs;
+static std::once_flag g_knobs_once;
 static int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
   return (e && *e) ? atoi(e) : dflt;
 }
+static void init_knobs() {
+  std::call_once(g_knobs_once, [] {
+    g_knobs.cta_group = env_int("GRPO_CTA_GROUP", g_knobs.cta_group) == 1 ? 1 : 2;
+    g_knobs.fwd_panel = env_int("GRPO_FWD_PANEL", g_knobs.fwd_panel);
+    g_knobs.sync_fwd = env_int("GRPO_SYNC_FWD", g_knobs.sync_fwd);
+    g_knobs.sync_dh = env_int("GRPO_SYNC_DH", g_knobs.sync_dh);
+    g_knobs.sync_dw = env_int("GRPO_SYNC_DW", g_knobs.sync_dw);
+    g_knobs.l2_hints = env_int("GRPO_L2_HINTS", g_knobs.l2_hints);
+    g_knobs.dh_m_fast = env_int("GRPO_DH_M_FAST", g_knobs.dh_m_fast);
+    g_knobs.chunk_rows = env_int("GRPO_CHUNK_ROWS", g_knobs.chunk_rows);
+  });
+}
+
+struct DevInfo : Knobs {
+  int sms = 0;
+};
 static int get_dev(DevInfo* out) {
-  static DevInfo cached[64];
-  static bool have[64] = {};
+  static int sms_cache[64] = {};
+  init_knobs();
   int dev = 0;
   GRPO_CUDA(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64) return fail(GRPO_ERR_ARG, "device ordinal out of range");
-  if (!have[dev]) {
+  if (sms_cache[dev] == 0) {
     cudaDeviceProp p;
     GRPO_CUDA(cudaGetDeviceProperties(&p, dev));
     if (p.major != 10) return fail(GRPO_ERR_ARG, "this library targets sm_100a (B200); found sm_%d%d", p.major, p.minor);
-    cached[dev].sms = p.multiProcessorCount;
-    const char* e = getenv("GRPO_CTA_GROUP");
-    cached[dev].cta_group = (e && e[0] == '1') ? 1 : 2;
-    cached[dev].fwd_panel = env_int("GRPO_FWD_PANEL", cached[dev].fwd_panel);
-    cached[dev].sync_fwd = env_int("GRPO_SYNC_FWD", cached[dev].sync_fwd);
-    cached[dev].sync_dh = env_int("GRPO_SYNC_DH", cached[dev].sync_dh);
-    cached[dev].sync_dw = env_int("GRPO_SYNC_DW", cached[dev].sync_dw);
-    have[dev] = true;
+    sms_cache[dev] = p.multiProcessorCount;
   }
-  *out = cached[dev];
+  static_cast<Knobs&>(*out) = g_knobs;
+  out->sms = sms_cache[dev];
   return 0;
 }
 
 // ------------------------------------------------------------------------------------------ GEMM launch
-template <int kCta, int BLOCK_N, int kStages, bool kAMn, bool kBMn, class Epi>
+template <int kCta, int BLOCK_N, int kStages, int kAMode, bool kBMn, class Epi>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const TileSched& sched,
                        const typename Epi::Params& ep, int sms, cudaStream_t stream) {
-  using Cfg = GemmCfg<kCta, BLOCK_N, kStages, kAMn, kBMn>;
-  auto kern = gemm_kernel<kCta, BLOCK_N, kStages, kAMn, kBMn, Epi>;
+  using Cfg = GemmCfg<kCta, BLOCK_N, kStages>;
+  auto kern = gemm_kernel<kCta, BLOCK_N, kStages, kAMode, kBMn, Epi>;
   const size_t smem = Cfg::smem_bytes(Epi::kSmemBytes);
   GRPO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   const uint32_t tiles = sched.m_blocks * sched.n_blocks;
@@ -207,40 +247,50 @@ static inline uint32_t cdiv(uint64_t a, uint64_t b) { return static_cast<uint32_
 // Rows per chunk of the chunked lm_head pipeline: 37 row-blocks of 256. With 74 CTA pairs, 37 x (H/256) output tiles
 // of the dHidden GEMM is a whole number of waves for H = 2048 (4) and H = 3584 (7); the chunk's exp-stash is
 // 9472 x V bf16 (2.9 GB at V = 151936).
-constexpr int64_t kChunkRows = 9472;
+constexpr int64_t kChunkRowsDefault = 9472;
 
-template <bool kAMn, bool kBMn, class Epi1, class Epi2>
+template <int kAMode, bool kBMn, class Epi1, class Epi2>
 static int launch_gemm_any(int cta_group, const void* a, uint64_t a_rows, uint64_t a_pitch, const void* b,
                            uint64_t b_rows, uint64_t b_pitch, uint64_t k, TileSched sched,
                            const typename Epi1::Params& ep1, const typename Epi2::Params& ep2, int sms,
                            cudaStream_t stream) {
   CUtensorMap ta, tb;
-  GRPO_TRY(make_operand_tmap(&ta, a, a_rows, k, a_pitch, kAMn, kBlockM));
-  GRPO_TRY(make_operand_tmap(&tb, b, b_rows, k, b_pitch, kBMn, kBlockN / cta_group));
+  GRPO_TRY(make_operand_tmap(&ta, a, a_rows, k, a_pitch, kAMode, kBlockM));
+  GRPO_TRY(make_operand_tmap(&tb, b, b_rows, k, b_pitch, kBMn ? A_MN_MAJOR : A_K_MAJOR, kBlockN / cta_group));
   sched.m_blocks = cdiv(a_rows, kBlockM * cta_group);
   sched.n_blocks = cdiv(b_rows, kBlockN);
   sched.k_blocks = cdiv(k, kBlockK);
   if (sched.panel_m == 0 || sched.panel_m > sched.m_blocks) sched.panel_m = sched.m_blocks;
-  if (cta_group == 1) return launch_gemm<1, kBlockN, kStages1, kAMn, kBMn, Epi1>(ta, tb, sched, ep1, sms, stream);
-  return launch_gemm<2, kBlockN, kStages2, kAMn, kBMn, Epi2>(ta, tb, sched, ep2, sms, stream);
+  if (sched.hint_a == 0) sched.hint_a = kEvictNormal;
+  if (sched.hint_b == 0) sched.hint_b = kEvictNormal;
+  if (cta_group == 1) return launch_gemm<1, kBlockN, kStages1, kAMode, kBMn, Epi1>(ta, tb, sched, ep1, sms, stream);
+  return launch_gemm<2, kBlockN, kStages2, kAMode, kBMn, Epi2>(ta, tb, sched, ep2, sms, stream);
 }
 
 // ------------------------------------------------------------------------------------------ workspace
 struct Workspace {
-  // sizes for one chunk
+  // sizes for one chunk of rows
   int64_t chunk_rows = 0, rows_pad = 0, n_tiles = 0;
+  int64_t stash_vb = 0;                // 64-column blocks per stash row block = ceil(V / 64)
+  // exp(z - z_label) (entropy-gradient mode: rewritten to dL/dz), BLOCKED: [rows_pad/64][stash_vb][64 rows][64 cols].
+  // 8 KB contiguous per block, so both backward GEMMs - one walking vocab blocks as K, the other row blocks as K -
+  // stream it from HBM in whole DRAM pages instead of 128-byte pieces 300 KB apart.
   __nv_bfloat16* stash = nullptr;
-  float *part_max = nullptr, *part_sum = nullptr, *part_ez = nullptr;
-  float *target_z = nullptr, *lse = nullptr, *dlogp = nullptr, *dent = nullptr, *ent = nullptr;
+  __nv_bfloat16* hd_scaled = nullptr;  // [chunk_rows][H] row-scaled hidden: B operand of the dW GEMM
+  float *part_sum = nullptr, *part_ez = nullptr;  // [n_tiles][rows_pad]
+  float *a_label = nullptr, *lse = nullptr, *inv_sum = nullptr, *dlogp = nullptr, *dent = nullptr, *ent = nullptr;
+  float *row_scale = nullptr, *onehot = nullptr;
   double* acc = nullptr;
   uint32_t* sync = nullptr;  // progress-barrier counters, one per GEMM of the chunk pipeline
   size_t bytes = 0;
 };
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-static Workspace carve(void* base, int64_t rows, int64_t vocab, bool with_stash) {
+static Workspace carve(void* base, int64_t rows, int64_t hdim, int64_t vocab, bool with_stash) {
   Workspace w;
-  w.chunk_rows = rows < kChunkRows ? rows : kChunkRows;
+  init_knobs();
+  const int64_t chunk_cap = g_knobs.chunk_rows > 0 ? g_knobs.chunk_rows : kChunkRowsDefault;
+  w.chunk_rows = rows < chunk_cap ? rows : chunk_cap;
   if (w.chunk_rows < 1) w.chunk_rows = 1;
   w.rows_pad = static_cast<int64_t>(align_up(static_cast<size_t>(w.chunk_rows), 256));
   w.n_tiles = (vocab + kBlockN - 1) / kBlockN;
@@ -251,17 +301,23 @@ static Workspace carve(void* base, int64_t rows, int64_t vocab, bool with_stash)
     off = align_up(off + nbytes, 1024);
     return r;
   };
-  if (with_stash) w.stash = reinterpret_cast<__nv_bfloat16*>(take(static_cast<size_t>(w.chunk_rows) * vocab * 2));
+  w.stash_vb = (vocab + 63) / 64;
+  if (with_stash) {
+    w.stash = reinterpret_cast<__nv_bfloat16*>(take(static_cast<size_t>(w.rows_pad) * w.stash_vb * 64 * 2));
+    w.hd_scaled = reinterpret_cast<__nv_bfloat16*>(take(static_cast<size_t>(w.chunk_rows) * hdim * 2));
+  }
   const size_t part = static_cast<size_t>(w.n_tiles) * w.rows_pad * 4;
-  w.part_max = reinterpret_cast<float*>(take(part));
   w.part_sum = reinterpret_cast<float*>(take(part));
   w.part_ez = reinterpret_cast<float*>(take(part));
   const size_t vec = static_cast<size_t>(w.rows_pad) * 4;
-  w.target_z = reinterpret_cast<float*>(take(vec));
+  w.a_label = reinterpret_cast<float*>(take(vec));
   w.lse = reinterpret_cast<float*>(take(vec));
+  w.inv_sum = reinterpret_cast<float*>(take(vec));
   w.dlogp = reinterpret_cast<float*>(take(vec));
   w.dent = reinterpret_cast<float*>(take(vec));
   w.ent = reinterpret_cast<float*>(take(vec));
+  w.row_scale = reinterpret_cast<float*>(take(vec));
+  w.onehot = reinterpret_cast<float*>(take(vec));
   w.acc = reinterpret_cast<double*>(take(ACC_N * sizeof(double)));
   w.sync = reinterpret_cast<uint32_t*>(take(64));
   w.bytes = off;
@@ -279,84 +335,108 @@ static int check_head_args(const void* hidden, const void* weight, int64_t rows,
 }
 
 // ------------------------------------------------------------------------------------------ chunk steps
-// logits GEMM + softmax statistics (+ optional exp stash) + per-row combine for rows [r0, r0 + n)
+// label logit -> logits GEMM + softmax sums (+ optional exp stash) -> per-row combine, for rows [r0, r0 + n)
 static int chunk_forward(const DevInfo& dev, const Workspace& w, const __nv_bfloat16* hidden,
                          const __nv_bfloat16* weight, const int64_t* labels, int64_t r0, int64_t n, int64_t h,
                          int64_t v, float temperature, bool want_entropy, bool want_stash, float* logp_out,
                          float* ent_out, float* lse_out, cudaStream_t stream) {
+  {
+    PhaseScope ps(PH_ROW_STATS, stream);
+    label_dot_kernel<<<cdiv(n * 32, 256), 256, 0, stream>>>(hidden + r0 * h, weight, labels + r0,
+                                                            static_cast<uint32_t>(n), static_cast<uint32_t>(h),
+                                                            static_cast<uint32_t>(v), w.a_label);
+    count_launch();
+    GRPO_CUDA(cudaGetLastError());
+  }
   EpiSoftmax<1, kBlockN>::Params p1;
   p1.rows = static_cast<uint32_t>(n);
   p1.vocab = static_cast<uint32_t>(v);
   p1.rows_pad = static_cast<uint32_t>(w.rows_pad);
   p1.scale = 1.f / temperature;
-  p1.part_max = w.part_max;
+  p1.ref = w.a_label;
   p1.part_sum = w.part_sum;
   p1.part_ez = want_entropy ? w.part_ez : nullptr;
-  p1.labels = labels + r0;
-  p1.target_z = w.target_z;
   p1.stash = want_stash ? w.stash : nullptr;
-  p1.ld_stash = v;
+  p1.stash_vb = static_cast<uint32_t>(w.stash_vb);
   EpiSoftmax<2, kBlockN>::Params p2;
-  memcpy(&p2, &p1, sizeof(p1));
   static_assert(sizeof(p1) == sizeof(p2), "epilogue params layout");
-  GRPO_CUDA(cudaMemsetAsync(w.target_z, 0, static_cast<size_t>(n) * 4, stream));
+  memcpy(&p2, &p1, sizeof(p1));
   TileSched s{};
   s.m_fast = 1;  // walk the row blocks of a panel under one vocab tile: the hidden panel stays in L2, W streams by
   s.panel_m = static_cast<uint32_t>(dev.fwd_panel * (dev.cta_group == 1 ? 2 : 1));  // counted in blocks of 128 * cta_group
   s.sync_period = static_cast<uint32_t>(dev.sync_fwd);
   s.sync_ctr = w.sync;
+  if (dev.l2_hints & 1) {  // the hidden panel is re-read under every vocab tile; a W tile is dead after one panel pass
+    s.hint_a = kEvictLast;
+    s.hint_b = kEvictFirst;
+  }
   GRPO_CUDA(cudaMemsetAsync(w.sync, 0, 64, stream));
   {
     PhaseScope ps(PH_LOGITS_GEMM, stream);
-    GRPO_TRY((launch_gemm_any<false, false, EpiSoftmax<1, kBlockN>, EpiSoftmax<2, kBlockN>>(
+    GRPO_TRY((launch_gemm_any<A_K_MAJOR, false, EpiSoftmax<1, kBlockN>, EpiSoftmax<2, kBlockN>>(
         dev.cta_group, hidden + r0 * h, n, h, weight, v, h, h, s, p1, p2, dev.sms, stream)));
   }
-  PhaseScope ps(PH_COMBINE, stream);
-  const uint32_t threads = 128;
-  combine_rows_kernel<<<cdiv(n, threads), threads, 0, stream>>>(
-      w.part_max, w.part_sum, want_entropy ? w.part_ez : nullptr, w.target_z, labels + r0, static_cast<uint32_t>(n),
-      static_cast<uint32_t>(w.rows_pad), static_cast<uint32_t>(w.n_tiles), static_cast<uint32_t>(v), lse_out,
-      logp_out, ent_out);
+  PhaseScope ps(PH_ROW_STATS, stream);
+  combine_rows_kernel<<<cdiv(n, 32), dim3(32, 8), 0, stream>>>(
+      w.part_sum, want_entropy ? w.part_ez : nullptr, w.a_label, labels + r0, static_cast<uint32_t>(n),
+      static_cast<uint32_t>(w.rows_pad), static_cast<uint32_t>(w.n_tiles), static_cast<uint32_t>(v), 1.f / temperature,
+      lse_out, logp_out, ent_out, w.inv_sum);
   count_launch();
   GRPO_CUDA(cudaGetLastError());
   return 0;
 }
 
-// stash -> dlogits, dHidden = dlogits . W, dW += dlogits^T . hidden for rows [r0, r0 + n)
+// dHidden = dlogits . W and dW += dlogits^T . hidden for rows [r0, r0 + n), from the stash of chunk_forward.
+//   dent == nullptr (the GRPO loss): dlogits factorises per row, the stash is used as is (scale_scatter_kernel).
+//   dent != nullptr (entropy gradient): the stash is first rewritten into dlogits (stash_to_dlogits_kernel).
 static int chunk_backward(const DevInfo& dev, const Workspace& w, const __nv_bfloat16* hidden,
                           const __nv_bfloat16* weight, const int64_t* labels, const float* dlogp, const float* dent,
-                          const float* ent, const float* lse, int64_t r0, int64_t n, int64_t h, int64_t v,
-                          float temperature, __nv_bfloat16* dhidden, float* dweight, cudaStream_t stream) {
+                          const float* ent, int64_t r0, int64_t n, int64_t h, int64_t v, float temperature,
+                          __nv_bfloat16* dhidden, float* dweight, cudaStream_t stream) {
+  const bool factorised = dent == nullptr;
+  const uint32_t un = static_cast<uint32_t>(n), uh = static_cast<uint32_t>(h), uv = static_cast<uint32_t>(v);
   {
-    PhaseScope ps(PH_TRANSFORM, stream);
-    dim3 grid(cdiv(v / 8, 256 * 4), static_cast<uint32_t>(n < 65535 ? n : 65535));
-    stash_to_dlogits_kernel<kBlockN><<<grid, 256, 0, stream>>>(
-        w.stash, v, static_cast<uint32_t>(n), static_cast<uint32_t>(v), w.part_max, static_cast<uint32_t>(w.rows_pad),
-        lse, dlogp, dent, ent, labels + r0, 1.f / temperature);
+    PhaseScope ps(PH_GRAD_PREP, stream);
+    if (factorised) {
+      scale_scatter_kernel<<<cdiv(n * 32, 256), 256, 0, stream>>>(hidden + r0 * h, labels + r0, dlogp, w.inv_sum,
+                                                                  1.f / temperature, un, uh, uv, w.row_scale, w.onehot,
+                                                                  w.hd_scaled, dweight);
+    } else {
+      dim3 grid(cdiv(v / 8, 256 * 4), un < 65535u ? un : 65535u);
+      stash_to_dlogits_kernel<<<grid, 256, 0, stream>>>(w.stash, static_cast<uint32_t>(w.stash_vb), un, uv, w.inv_sum,
+                                                        dlogp, dent, ent, labels + r0, 1.f / temperature);
+    }
     count_launch();
     GRPO_CUDA(cudaGetLastError());
   }
-  {  // dHidden[n][h] = G[n][v] . W[v][h]       A = G (K-major), B = W read "transposed" (MN-major)
+  {  // dHidden[n][h] = row_scale * (E[n][v] . W[v][h]) + onehot * W[label]   A = stash (K-major), B = W read transposed
     PhaseScope ps(PH_DH_GEMM, stream);
-    EpiBF16<1, kBlockN>::Params p1{dhidden + r0 * h, h, static_cast<uint32_t>(n), static_cast<uint32_t>(h)};
-    EpiBF16<2, kBlockN>::Params p2{dhidden + r0 * h, h, static_cast<uint32_t>(n), static_cast<uint32_t>(h)};
+    EpiBF16<1, kBlockN>::Params p1{dhidden + r0 * h, h, un, uh, factorised ? w.row_scale : nullptr,
+                                   factorised ? w.onehot : nullptr, labels + r0, weight, h};
+    EpiBF16<2, kBlockN>::Params p2{dhidden + r0 * h, h, un, uh, factorised ? w.row_scale : nullptr,
+                                   factorised ? w.onehot : nullptr, labels + r0, weight, h};
     TileSched s{};
-    s.m_fast = 0;  // all H column blocks of a few row blocks run together: W streams once per wave
+    s.m_fast = static_cast<uint32_t>(dev.dh_m_fast);  // 0: all H column blocks of a few row blocks run together
     s.sync_period = static_cast<uint32_t>(dev.sync_dh);
     s.sync_ctr = w.sync + 1;
-    GRPO_TRY((launch_gemm_any<false, true, EpiBF16<1, kBlockN>, EpiBF16<2, kBlockN>>(
-        dev.cta_group, w.stash, n, v, weight, h, h, v, s, p1, p2, dev.sms, stream)));
+    GRPO_TRY((launch_gemm_any<A_BLOCKED_K, true, EpiBF16<1, kBlockN>, EpiBF16<2, kBlockN>>(
+        dev.cta_group, w.stash, n, w.stash_vb, weight, h, h, v, s, p1, p2, dev.sms, stream)));
   }
-  {  // dW[v][h] += G^T[v][n] . hidden[n][h]    A = G read transposed (MN-major), B = hidden read transposed
+  {  // dW[v][h] += E^T[v][n] . hd[n][h]    A = stash read transposed (MN-major), B = (scaled) hidden read transposed
     PhaseScope ps(PH_DW_GEMM, stream);
-    EpiF32<1, kBlockN>::Params p1{dweight, h, static_cast<uint32_t>(v), static_cast<uint32_t>(h), 1u};
-    EpiF32<2, kBlockN>::Params p2{dweight, h, static_cast<uint32_t>(v), static_cast<uint32_t>(h), 1u};
+    EpiF32<1, kBlockN>::Params p1{dweight, h, uv, uh, 1u};
+    EpiF32<2, kBlockN>::Params p2{dweight, h, uv, uh, 1u};
     TileSched s{};
-    s.m_fast = 0;  // the H column blocks of one vocab block run together: the G panel is read from HBM once
+    s.m_fast = 0;  // the H column blocks of one vocab block run together: the stash panel is read from HBM once
     s.sync_period = static_cast<uint32_t>(dev.sync_dw);
     s.sync_ctr = w.sync + 2;
-    GRPO_TRY((launch_gemm_any<true, true, EpiF32<1, kBlockN>, EpiF32<2, kBlockN>>(
-        dev.cta_group, w.stash, v, v, hidden + r0 * h, h, h, n, s, p1, p2, dev.sms, stream)));
+    if (dev.l2_hints & 2) {  // the (scaled) hidden chunk is re-read for every vocab block; the stash streams through once
+      s.hint_a = kEvictFirst;
+      s.hint_b = kEvictLast;
+    }
+    const __nv_bfloat16* b_op = factorised ? w.hd_scaled : hidden + r0 * h;
+    GRPO_TRY((launch_gemm_any<A_BLOCKED_MN, true, EpiF32<1, kBlockN>, EpiF32<2, kBlockN>>(
+        dev.cta_group, w.stash, v, w.stash_vb, b_op, h, h, n, s, p1, p2, dev.sms, stream)));
   }
   return 0;
 }
@@ -389,6 +469,21 @@ int grpo_abi_version(void) { return 1; }
 const char* grpo_last_error(void) { return g_err; }
 long long grpo_launch_count(void) { return g_launches.load(); }
 
+int grpo_set_option(const char* name, int value) {
+  init_knobs();
+  if (!name) return fail(GRPO_ERR_ARG, "null option name");
+  if (!strcmp(name, "cta_group")) g_knobs.cta_group = value == 1 ? 1 : 2;
+  else if (!strcmp(name, "fwd_panel")) g_knobs.fwd_panel = value > 0 ? value : 19;
+  else if (!strcmp(name, "sync_fwd")) g_knobs.sync_fwd = value;
+  else if (!strcmp(name, "sync_dh")) g_knobs.sync_dh = value;
+  else if (!strcmp(name, "sync_dw")) g_knobs.sync_dw = value;
+  else if (!strcmp(name, "l2_hints")) g_knobs.l2_hints = value;
+  else if (!strcmp(name, "dh_m_fast")) g_knobs.dh_m_fast = value;
+  else if (!strcmp(name, "chunk_rows")) g_knobs.chunk_rows = value > 0 ? (value + 255) / 256 * 256 : 9472;
+  else return fail(GRPO_ERR_ARG, "unknown option '%s'", name);
+  return 0;
+}
+
 int grpo_profile_enable(int on) {
   g_prof.on.store(on != 0);
   return 0;
@@ -416,14 +511,14 @@ int grpo_profile_read(double* ms_out, long long* count_out, int reset) {
   return 0;
 }
 
-size_t grpo_lmhead_fwd_workspace_bytes(int64_t rows, int64_t, int64_t vocab) {
-  return carve(nullptr, rows, vocab, false).bytes;
+size_t grpo_lmhead_fwd_workspace_bytes(int64_t rows, int64_t hidden_dim, int64_t vocab) {
+  return carve(nullptr, rows, hidden_dim, vocab, false).bytes;
 }
-size_t grpo_lmhead_bwd_workspace_bytes(int64_t rows, int64_t, int64_t vocab) {
-  return carve(nullptr, rows, vocab, true).bytes;
+size_t grpo_lmhead_bwd_workspace_bytes(int64_t rows, int64_t hidden_dim, int64_t vocab) {
+  return carve(nullptr, rows, hidden_dim, vocab, true).bytes;
 }
-size_t grpo_fused_loss_workspace_bytes(int64_t rows, int64_t, int64_t vocab) {
-  return carve(nullptr, rows, vocab, true).bytes;
+size_t grpo_fused_loss_workspace_bytes(int64_t rows, int64_t hidden_dim, int64_t vocab) {
+  return carve(nullptr, rows, hidden_dim, vocab, true).bytes;
 }
 
 int grpo_lmhead_logprob_fwd(const void* hidden, const void* weight, const int64_t* labels, int64_t rows,
@@ -434,7 +529,7 @@ int grpo_lmhead_logprob_fwd(const void* hidden, const void* weight, const int64_
   if (!labels || !logp) return fail(GRPO_ERR_ARG, "labels / logp must not be null");
   DevInfo dev;
   GRPO_TRY(get_dev(&dev));
-  const Workspace w = carve(workspace, rows, vocab, false);
+  const Workspace w = carve(workspace, rows, hidden_dim, vocab, false);
   if (!workspace || workspace_bytes < w.bytes)
     return fail(GRPO_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
   auto* hp = static_cast<const __nv_bfloat16*>(hidden);
@@ -456,7 +551,7 @@ int grpo_lmhead_bwd(const void* hidden, const void* weight, const int64_t* label
     return fail(GRPO_ERR_ARG, "labels / dlogp / dhidden / dweight must not be null");
   DevInfo dev;
   GRPO_TRY(get_dev(&dev));
-  const Workspace w = carve(workspace, rows, vocab, true);
+  const Workspace w = carve(workspace, rows, hidden_dim, vocab, true);
   if (!workspace || workspace_bytes < w.bytes)
     return fail(GRPO_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
   auto* hp = static_cast<const __nv_bfloat16*>(hidden);
@@ -465,8 +560,8 @@ int grpo_lmhead_bwd(const void* hidden, const void* weight, const int64_t* label
     const int64_t n = (rows - r0 < w.chunk_rows) ? rows - r0 : w.chunk_rows;
     GRPO_TRY(chunk_forward(dev, w, hp, wp, labels, r0, n, hidden_dim, vocab, temperature, dentropy != nullptr, true,
                            nullptr, dentropy ? w.ent : nullptr, w.lse, stream));
-    GRPO_TRY(chunk_backward(dev, w, hp, wp, labels, dlogp + r0, dentropy ? dentropy + r0 : nullptr, w.ent, w.lse, r0,
-                            n, hidden_dim, vocab, temperature, static_cast<__nv_bfloat16*>(dhidden), dweight, stream));
+    GRPO_TRY(chunk_backward(dev, w, hp, wp, labels, dlogp + r0, dentropy ? dentropy + r0 : nullptr, w.ent, r0, n,
+                            hidden_dim, vocab, temperature, static_cast<__nv_bfloat16*>(dhidden), dweight, stream));
   }
   return 0;
 }
@@ -492,7 +587,7 @@ int grpo_fused_loss_fwd_bwd(const void* hidden, const void* weight, const int64_
   DevInfo dev;
   GRPO_TRY(get_dev(&dev));
   const bool want_bwd = dhidden != nullptr;
-  const Workspace w = carve(workspace, rows, vocab, true);
+  const Workspace w = carve(workspace, rows, hidden_dim, vocab, true);
   if (!workspace || workspace_bytes < w.bytes)
     return fail(GRPO_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
   LossCfg cfg = make_loss_cfg(clip_ratio_low, clip_ratio_high, clip_ratio_dual, kl_mode, kl_coef, grad_accum);
@@ -526,7 +621,7 @@ int grpo_fused_loss_fwd_bwd(const void* hidden, const void* weight, const int64_
     GRPO_CUDA(cudaGetLastError());
     if (want_bwd)
       GRPO_TRY(chunk_backward(dev, w, hp, wp, labels, w.dlogp, entropy_coef != 0.f ? w.dent : nullptr,
-                              want_ent ? entropy_out + r0 : nullptr, w.lse, r0, n, hidden_dim, vocab, temperature,
+                              want_ent ? entropy_out + r0 : nullptr, r0, n, hidden_dim, vocab, temperature,
                               static_cast<__nv_bfloat16*>(dhidden), dweight, stream));
   }
   loss_finalize_kernel<<<1, 32, 0, stream>>>(w.acc, cfg, metrics);
@@ -734,16 +829,25 @@ int grpo_debug_gemm(const void* a, const void* b, float* c, int64_t m, int64_t n
                                 static_cast<uint32_t>(accumulate != 0)};
   TileSched s{};
   s.m_fast = 1;
-  const uint64_t a_pitch = a_mn_major ? m : k, b_pitch = b_mn_major ? n : k;
+  // A: 0 = [m][k], 1 = [k][m], 2 = blocked [m/64][k/64][64][64], 3 = blocked [k/64][m/64][64 k][64 m]
+  const uint64_t a_pitch = a_mn_major == 0 ? k : (a_mn_major == 1 ? m : (a_mn_major == 2 ? (k + 63) / 64 : (m + 63) / 64));
+  const uint64_t b_pitch = b_mn_major ? n : k;
   using E1 = EpiF32<1, kBlockN>;
   using E2 = EpiF32<2, kBlockN>;
-  if (!a_mn_major && !b_mn_major)
-    return launch_gemm_any<false, false, E1, E2>(cta_group, a, m, a_pitch, b, n, b_pitch, k, s, p1, p2, dev.sms, stream);
-  if (!a_mn_major && b_mn_major)
-    return launch_gemm_any<false, true, E1, E2>(cta_group, a, m, a_pitch, b, n, b_pitch, k, s, p1, p2, dev.sms, stream);
-  if (a_mn_major && b_mn_major)
-    return launch_gemm_any<true, true, E1, E2>(cta_group, a, m, a_pitch, b, n, b_pitch, k, s, p1, p2, dev.sms, stream);
-  return launch_gemm_any<true, false, E1, E2>(cta_group, a, m, a_pitch, b, n, b_pitch, k, s, p1, p2, dev.sms, stream);
+#define GRPO_DBG(AM, BM) \
+  return launch_gemm_any<AM, BM, E1, E2>(cta_group, a, m, a_pitch, b, n, b_pitch, k, s, p1, p2, dev.sms, stream)
+  switch (a_mn_major * 2 + (b_mn_major ? 1 : 0)) {
+    case 0: GRPO_DBG(A_K_MAJOR, false);
+    case 1: GRPO_DBG(A_K_MAJOR, true);
+    case 2: GRPO_DBG(A_MN_MAJOR, false);
+    case 3: GRPO_DBG(A_MN_MAJOR, true);
+    case 4: GRPO_DBG(A_BLOCKED_K, false);
+    case 5: GRPO_DBG(A_BLOCKED_K, true);
+    case 6: GRPO_DBG(A_BLOCKED_MN, false);
+    case 7: GRPO_DBG(A_BLOCKED_MN, true);
+    default: return fail(GRPO_ERR_ARG, "a_mn_major must be 0..3");
+  }
+#undef GRPO_DBG
 }
 
 }  // extern "C"

@@ -1,5 +1,5 @@
-// lm_head kernels: the softmax-statistics epilogue of the logits GEMM, the per-row combine, and the in-place
-// transform of the stashed exp tile values into dL/dlogits.
+// lm_head kernels: the label-logit reference, the softmax-statistics epilogue of the logits GEMM, the per-row combine,
+// and the two ways of turning the stashed exponentials into the backward GEMMs' operands.
 //
 // Reference path being replaced (logits fully materialised there):
 //   verl/workers/actor/dp_actor.py:125-128   logits = lm_head(hidden); logits.div_(temperature); log_probs_from_logits
@@ -10,13 +10,46 @@
 namespace grpo {
 
 constexpr float kLog2e = 1.4426950408889634f;
+// exp2 argument clamp of the softmax epilogue: keeps every stashed value finite (2^100 ~ 1.3e30, row sums < 2e35) so that
+// masked rows can never inject inf * 0 = NaN into the backward GEMMs. It only binds when some logit exceeds the label's
+// logit by more than 69 nats, i.e. for a label whose probability is below e^-69 (1e-30); such a row's lse saturates.
+constexpr float kClampLog2 = 100.f;
 
 // ------------------------------------------------------------------------------------------
-// Forward epilogue. One thread owns one token row of the 128 x BLOCK_N accumulator tile:
-//   pass 1: tile max of the raw accumulator
-//   pass 2: e = exp(z - tile max) -> running sum, sum(e*z) (for the entropy), optional bf16 stash of e, and capture of
-//           the label logit if the label column falls in this tile
-// Per-(vocab tile, row) partials go to a [tiles][rows_pad] workspace; lse/entropy are finished by combine_rows_kernel.
+// Per-row reference for the softmax: the label's own logit a_label = h_r . W[label_r] (raw accumulator units, before
+// the 1/temperature scale), one warp per row. With it the forward epilogue is a single pass, exp(z - z_label) needs no
+// running max, log p[label] = -log sum_v exp(z_v - z_label), and the stash differs from the softmax only by a per-row
+// factor - which the backward GEMMs apply in their epilogue / operand instead of a separate pass over the stash.
+// ------------------------------------------------------------------------------------------
+__global__ void label_dot_kernel(const __nv_bfloat16* __restrict__ hidden, const __nv_bfloat16* __restrict__ weight,
+                                 const int64_t* __restrict__ labels, uint32_t rows, uint32_t hdim, uint32_t vocab,
+                                 float* __restrict__ a_label) {
+  const uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int64_t lab = labels[row];
+  float acc = 0.f;
+  if (lab >= 0 && lab < static_cast<int64_t>(vocab)) {
+    const uint4* hp = reinterpret_cast<const uint4*>(hidden + static_cast<size_t>(row) * hdim);
+    const uint4* wp = reinterpret_cast<const uint4*>(weight + static_cast<size_t>(lab) * hdim);
+    for (uint32_t i = lane; i < (hdim >> 3); i += 32) {
+      const uint4 a = hp[i], b = wp[i];
+      const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        acc = fmaf(__uint_as_float(aw[k] << 16), __uint_as_float(bw[k] << 16), acc);
+        acc = fmaf(__uint_as_float(aw[k] & 0xffff0000u), __uint_as_float(bw[k] & 0xffff0000u), acc);
+      }
+    }
+    acc = warp_sum(acc);
+  }
+  if (lane == 0) a_label[row] = acc;  // 0 for an out-of-range (ignored) label
+}
+
+// ------------------------------------------------------------------------------------------
+// Forward epilogue. One thread owns one token row of the 128 x BLOCK_N accumulator tile and makes ONE pass over it:
+//   e = exp((a - a_label) / T)  ->  sum e, sum e*z (for the entropy), optional bf16 stash of e.
+// Per-(vocab tile, row) partial sums go to a [tiles][rows_pad] workspace and are finished by combine_rows_kernel.
 // ------------------------------------------------------------------------------------------
 template <int kCta, int BLOCK_N>
 struct EpiSoftmax {
@@ -25,13 +58,11 @@ struct EpiSoftmax {
     uint32_t vocab;      // V
     uint32_t rows_pad;   // leading dimension of the partial arrays
     float scale;         // 1 / temperature
-    float* part_max;     // [n_tiles][rows_pad]  max_v z           (z = accumulator * scale)
-    float* part_sum;     // [n_tiles][rows_pad]  sum_v exp(z - max)
-    float* part_ez;      // [n_tiles][rows_pad]  sum_v exp(z - max) * z      (nullptr: skip)
-    const int64_t* labels;  // [rows]
-    float* target_z;        // [rows] z at the label column
-    __nv_bfloat16* stash;   // [rows][ld_stash] exp(z - tile max) in bf16    (nullptr: forward only)
-    int64_t ld_stash;
+    const float* ref;    // [rows] a_label (label_dot_kernel)
+    float* part_sum;     // [n_tiles][rows_pad]  sum_v exp(z - z_label)
+    float* part_ez;      // [n_tiles][rows_pad]  sum_v exp(z - z_label) * z      (nullptr: skip)
+    __nv_bfloat16* stash;   // blocked [rows/64][stash_vb][64][64]: exp(z - z_label) in bf16 (nullptr: forward only)
+    uint32_t stash_vb;      // 64-column blocks per row block
   };
   static constexpr int kSmemBytes = 0;
 
@@ -40,61 +71,32 @@ struct EpiSoftmax {
     const bool row_ok = row < p.rows;
     const uint32_t col0 = c.n_blk * BLOCK_N;
     const uint32_t ncols = min(static_cast<uint32_t>(BLOCK_N), p.vocab - col0);
-    const uint32_t ngroups = (ncols + 31) >> 5;
+    const uint32_t ngroups = (ncols + 31) >> 5;  // column groups of 32 that hold at least one real vocabulary entry
+    const float c1 = p.scale * kLog2e;
+    const float off = (row_ok ? p.ref[row] : 0.f) * c1;
+    const bool want_ez = p.part_ez != nullptr;
+    // Every row of the tile is stored (zeros past the last token / past the vocabulary) so that the blocked stash
+    // never exposes stale bytes to the backward GEMMs' zero-padded K tails.
+    const bool want_stash = p.stash != nullptr;
+    __nv_bfloat16* srow = want_stash
+        ? p.stash + (static_cast<size_t>(row >> 6) * p.stash_vb + (col0 >> 6)) * 4096 + (row & 63) * 64
+        : nullptr;
+    const uint32_t store_groups = want_stash ? min(static_cast<uint32_t>(BLOCK_N / 32), 2 * (p.stash_vb - (col0 >> 6))) : 0;
 
-    // ---- pass 1: tile max
-    float mx = -INFINITY;
+    float s0 = 0.f, s1 = 0.f, t0 = 0.f, t1 = 0.f;
 #pragma unroll 1
     for (uint32_t g = 0; g < ngroups; ++g) {
       uint32_t v[32];
       tmem_ld_32x32(c.tmem_acc + g * 32, v);
       tmem_ld_wait();
       const uint32_t valid = ncols - g * 32;  // >= 1
-      if (valid >= 32) {
-        float m0 = __uint_as_float(v[0]), m1 = __uint_as_float(v[1]), m2 = __uint_as_float(v[2]),
-              m3 = __uint_as_float(v[3]);
-#pragma unroll
-        for (int i = 4; i < 32; i += 4) {
-          m0 = fmaxf(m0, __uint_as_float(v[i]));
-          m1 = fmaxf(m1, __uint_as_float(v[i + 1]));
-          m2 = fmaxf(m2, __uint_as_float(v[i + 2]));
-          m3 = fmaxf(m3, __uint_as_float(v[i + 3]));
-        }
-        mx = fmaxf(mx, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (static_cast<uint32_t>(i) < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
-      }
-    }
-    // scale > 0, so max commutes with the temperature scaling
-    const float c1 = p.scale * kLog2e;
-    const float off = mx * c1;
-
-    int32_t tl = -1;  // label column relative to this tile, if it lands here
-    if (row_ok) {
-      const int64_t lab = p.labels[row] - static_cast<int64_t>(col0);
-      if (lab >= 0 && lab < static_cast<int64_t>(ncols)) tl = static_cast<int32_t>(lab);
-    }
-    const bool want_ez = p.part_ez != nullptr;
-    const bool want_stash = p.stash != nullptr;
-    __nv_bfloat16* srow = want_stash ? p.stash + static_cast<int64_t>(row) * p.ld_stash + col0 : nullptr;
-
-    // ---- pass 2: exp, sums, stash, label capture
-    float s0 = 0.f, s1 = 0.f, t0 = 0.f, t1 = 0.f, zt = 0.f;
-#pragma unroll 1
-    for (uint32_t g = 0; g < ngroups; ++g) {
-      uint32_t v[32];
-      tmem_ld_32x32(c.tmem_acc + g * 32, v);
-      tmem_ld_wait();
-      const uint32_t valid = ncols - g * 32;
       float e[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        const float a = __uint_as_float(v[i]);
-        float ex = fast_exp2(fmaf(a, c1, -off));
-        if (valid < 32 && static_cast<uint32_t>(i) >= valid) ex = 0.f;
-        e[i] = ex;
+        const float x = fminf(fmaf(__uint_as_float(v[i]), c1, -off), kClampLog2);
+        float ex = fast_exp2(x);
+        if (valid < 32 && static_cast<uint32_t>(i) >= valid) ex = 0.f;  // zero-filled columns past the vocabulary
+        e[i] = row_ok ? ex : 0.f;
       }
 #pragma unroll
       for (int i = 0; i < 32; i += 2) {
@@ -108,93 +110,151 @@ struct EpiSoftmax {
           t1 = fmaf(e[i + 1], __uint_as_float(v[i + 1]), t1);
         }
       }
-      if (__any_sync(0xffffffffu, (tl >> 5) == static_cast<int32_t>(g) && tl >= 0)) {
-        const int32_t j = tl - static_cast<int32_t>(g * 32);
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (j == i) zt = __uint_as_float(v[i]);
-      }
-      if (want_stash && row_ok) {
+      if (want_stash) {
+        __nv_bfloat16* dst = srow + (g >> 1) * 4096 + (g & 1) * 32;  // 64-column block g/2, half g%2 of its 128-byte row
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          if (static_cast<uint32_t>(q * 8) < valid) {  // vocab % 8 == 0
-            uint4 pk;
-            pk.x = pack_bf16x2(e[8 * q + 0], e[8 * q + 1]);
-            pk.y = pack_bf16x2(e[8 * q + 2], e[8 * q + 3]);
-            pk.z = pack_bf16x2(e[8 * q + 4], e[8 * q + 5]);
-            pk.w = pack_bf16x2(e[8 * q + 6], e[8 * q + 7]);
-            *reinterpret_cast<uint4*>(srow + g * 32 + q * 8) = pk;
-          }
+          uint4 pk;
+          pk.x = pack_bf16x2(e[8 * q + 0], e[8 * q + 1]);
+          pk.y = pack_bf16x2(e[8 * q + 2], e[8 * q + 3]);
+          pk.z = pack_bf16x2(e[8 * q + 4], e[8 * q + 5]);
+          pk.w = pack_bf16x2(e[8 * q + 6], e[8 * q + 7]);
+          __stcs(reinterpret_cast<uint4*>(dst + q * 8), pk);  // streamed: keep the hidden panel in L2
         }
       }
     }
+    // column groups of the last vocabulary block that lie wholly past the vocabulary: zeros
+    for (uint32_t g = ngroups; g < store_groups; ++g) {
+      __nv_bfloat16* dst = srow + (g >> 1) * 4096 + (g & 1) * 32;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) __stcs(reinterpret_cast<uint4*>(dst + q * 8), make_uint4(0u, 0u, 0u, 0u));
+    }
     if (row_ok) {
       const size_t o = static_cast<size_t>(c.n_blk) * p.rows_pad + row;
-      p.part_max[o] = mx * p.scale;
       p.part_sum[o] = s0 + s1;
       if (want_ez) p.part_ez[o] = (t0 + t1) * p.scale;
-      if (tl >= 0) p.target_z[row] = zt * p.scale;
     }
   }
 };
 
 // ------------------------------------------------------------------------------------------
-// Per-row combine of the vocab-tile partials: lse, log p[label], entropy = lse - sum p z.
+// Per-row combine of the vocab-tile partial sums. blockDim = (32 rows, 8 tile slices).
+//   S = sum_v exp(z_v - z_label);  lse = z_label + log S;  log p[label] = -log S;  entropy = lse - (sum e z) / S
 // ------------------------------------------------------------------------------------------
-__global__ void combine_rows_kernel(const float* __restrict__ part_max, const float* __restrict__ part_sum,
-                                    const float* __restrict__ part_ez, const float* __restrict__ target_z,
-                                    const int64_t* __restrict__ labels, uint32_t rows, uint32_t rows_pad,
-                                    uint32_t n_tiles, uint32_t vocab, float* __restrict__ lse_out,
-                                    float* __restrict__ logp_out, float* __restrict__ ent_out) {
-  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= rows) return;
-  float m = -INFINITY;
-  for (uint32_t j = 0; j < n_tiles; ++j) m = fmaxf(m, part_max[static_cast<size_t>(j) * rows_pad + r]);
-  float s = 0.f, ez = 0.f;
-  for (uint32_t j = 0; j < n_tiles; ++j) {
-    const size_t o = static_cast<size_t>(j) * rows_pad + r;
-    const float w = __expf(part_max[o] - m);
-    s = fmaf(part_sum[o], w, s);
-    if (part_ez) ez = fmaf(part_ez[o], w, ez);
+__global__ void combine_rows_kernel(const float* __restrict__ part_sum, const float* __restrict__ part_ez,
+                                    const float* __restrict__ a_label, const int64_t* __restrict__ labels,
+                                    uint32_t rows, uint32_t rows_pad, uint32_t n_tiles, uint32_t vocab, float scale,
+                                    float* __restrict__ lse_out, float* __restrict__ logp_out,
+                                    float* __restrict__ ent_out, float* __restrict__ inv_sum_out) {
+  __shared__ float red_s[8][33], red_t[8][33];
+  const uint32_t r = blockIdx.x * 32 + threadIdx.x;
+  float s = 0.f, t = 0.f;
+  if (r < rows) {
+    for (uint32_t j = threadIdx.y; j < n_tiles; j += 8) {
+      const size_t o = static_cast<size_t>(j) * rows_pad + r;
+      s += part_sum[o];
+      if (part_ez) t += part_ez[o];
+    }
   }
-  const float lse = m + logf(s);
+  red_s[threadIdx.y][threadIdx.x] = s;
+  red_t[threadIdx.y][threadIdx.x] = t;
+  __syncthreads();
+  if (threadIdx.y != 0 || r >= rows) return;
+#pragma unroll
+  for (int k = 1; k < 8; ++k) {
+    s += red_s[k][threadIdx.x];
+    t += red_t[k][threadIdx.x];
+  }
+  const float log_s = logf(s);
+  const float lse = a_label[r] * scale + log_s;
   if (lse_out) lse_out[r] = lse;
   if (logp_out) {  // a label outside [0, vocab) (e.g. an ignore index) yields 0, like the cross-entropy it replaces
     const int64_t lab = labels[r];
-    logp_out[r] = (lab >= 0 && lab < static_cast<int64_t>(vocab)) ? target_z[r] - lse : 0.f;
+    logp_out[r] = (lab >= 0 && lab < static_cast<int64_t>(vocab)) ? -log_s : 0.f;
   }
-  if (ent_out) ent_out[r] = lse - ez / s;
+  if (ent_out) ent_out[r] = lse - t / s;
+  if (inv_sum_out) inv_sum_out[r] = 1.f / s;
 }
 
 // ------------------------------------------------------------------------------------------
-// stash (exp(z - tile max), bf16)  ->  dL/dz in place (bf16):
-//    p[r][v]  = exp(tile max - lse r) * e[r][v]
-//    dz[r][v] = scale * ( dlogp[r] * (1[v == label r] - p) - dent[r] * p * (log p + H r) )
-// (the 1/temperature of z = h.W / T is folded in here, so the two backward GEMMs are plain products; the dent term is
-// the gradient of a per-token entropy output, H = lse - sum p z, and is skipped when dent == nullptr).
-// Rows whose upstream gradients are all zero (masked tokens) are written as zeros without reading the stash.
+// Fast backward preparation (no entropy gradient). With p = e / S the gradient of the logits factorises per row:
+//     dz[r][v] = (g_r / T) * (1[v == label_r] - e[r][v] / S_r)
+// so the stash is used AS IS by both backward GEMMs and only O(rows * H) work remains, done here, one warp per row:
+//     row_scale[r] = -g_r / (T S_r)          -> applied by the dHidden GEMM epilogue to (e . W)[r][:]
+//     onehot[r]    =  g_r / T                -> dHidden epilogue adds onehot[r] * W[label_r][:]
+//     hd_scaled[r] = bf16(row_scale[r] * hidden[r][:])      -> B operand of the dW GEMM:  dW += e^T . hd_scaled
+//     dW[label_r][:] += onehot[r] * hidden[r][:]            -> the one-hot part of dW (fp32 red.add)
 // ------------------------------------------------------------------------------------------
-template <int BLOCK_N>
-__global__ void stash_to_dlogits_kernel(__nv_bfloat16* __restrict__ stash, int64_t ld_stash, uint32_t rows,
-                                        uint32_t vocab, const float* __restrict__ part_max, uint32_t rows_pad,
-                                        const float* __restrict__ lse, const float* __restrict__ dlogp,
-                                        const float* __restrict__ dent, const float* __restrict__ ent,
-                                        const int64_t* __restrict__ labels, float scale) {
+__global__ void scale_scatter_kernel(const __nv_bfloat16* __restrict__ hidden, const int64_t* __restrict__ labels,
+                                     const float* __restrict__ dlogp, const float* __restrict__ inv_sum, float scale,
+                                     uint32_t rows, uint32_t hdim, uint32_t vocab, float* __restrict__ row_scale,
+                                     float* __restrict__ onehot, __nv_bfloat16* __restrict__ hd_scaled,
+                                     float* __restrict__ dweight) {
+  const uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float o = dlogp[row] * scale;
+  const float sc = -o * inv_sum[row];
+  const int64_t lab = labels[row];
+  const bool lab_ok = lab >= 0 && lab < static_cast<int64_t>(vocab);
+  if (lane == 0) {
+    row_scale[row] = sc;
+    onehot[row] = lab_ok ? o : 0.f;
+  }
+  const uint4* hp = reinterpret_cast<const uint4*>(hidden + static_cast<size_t>(row) * hdim);
+  uint4* op = reinterpret_cast<uint4*>(hd_scaled + static_cast<size_t>(row) * hdim);
+  float* dwp = (lab_ok && o != 0.f) ? dweight + static_cast<size_t>(lab) * hdim : nullptr;
+  for (uint32_t i = lane; i < (hdim >> 3); i += 32) {
+    uint4 out = make_uint4(0u, 0u, 0u, 0u);
+    if (sc != 0.f) {
+      const uint4 a = hp[i];
+      const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+      float f[8];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        f[2 * k] = __uint_as_float(aw[k] << 16);
+        f[2 * k + 1] = __uint_as_float(aw[k] & 0xffff0000u);
+      }
+      out.x = pack_bf16x2(f[0] * sc, f[1] * sc);
+      out.y = pack_bf16x2(f[2] * sc, f[3] * sc);
+      out.z = pack_bf16x2(f[4] * sc, f[5] * sc);
+      out.w = pack_bf16x2(f[6] * sc, f[7] * sc);
+      if (dwp) {
+        atomicAdd(reinterpret_cast<float4*>(dwp + i * 8), make_float4(f[0] * o, f[1] * o, f[2] * o, f[3] * o));
+        atomicAdd(reinterpret_cast<float4*>(dwp + i * 8 + 4), make_float4(f[4] * o, f[5] * o, f[6] * o, f[7] * o));
+      }
+    }
+    op[i] = out;  // masked rows (g == 0) contribute an all-zero operand row
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// General backward preparation (entropy gradient requested): stash -> dL/dz in place (bf16)
+//    p = e / S;   dz[r][v] = scale * ( dlogp[r] * (1[v == label r] - p) - dent[r] * p * (log p + H r) )
+// after which the backward GEMMs run with unit scales. Rows whose upstream gradients are all zero are written as zeros
+// without reading the stash.
+// ------------------------------------------------------------------------------------------
+__global__ void stash_to_dlogits_kernel(__nv_bfloat16* __restrict__ stash, uint32_t stash_vb, uint32_t rows,
+                                        uint32_t vocab, const float* __restrict__ inv_sum,
+                                        const float* __restrict__ dlogp, const float* __restrict__ dent,
+                                        const float* __restrict__ ent, const int64_t* __restrict__ labels,
+                                        float scale) {
   const uint32_t vecs_per_row = vocab >> 3;
   for (uint32_t r = blockIdx.y; r < rows; r += gridDim.y) {
     const float g = dlogp[r] * scale;
     const float ge = dent ? dent[r] * scale : 0.f;
     const float h = dent ? ent[r] : 0.f;
-    const float l = lse[r];
+    const float c = inv_sum[r];
+    const float log_c = __logf(c);
     const int64_t lab = labels[r];
-    uint4* rowp = reinterpret_cast<uint4*>(stash + static_cast<int64_t>(r) * ld_stash);
+    // blocked stash: row r lives in row block r/64; its 64-column block b starts b * 4096 elements further on
+    __nv_bfloat16* rowp = stash + static_cast<size_t>(r >> 6) * stash_vb * 4096 + (r & 63) * 64;
     for (uint32_t vi = blockIdx.x * blockDim.x + threadIdx.x; vi < vecs_per_row; vi += gridDim.x * blockDim.x) {
       uint4 out = make_uint4(0u, 0u, 0u, 0u);
+      const uint32_t col = vi << 3;
+      uint4* vecp = reinterpret_cast<uint4*>(rowp + static_cast<size_t>(col >> 6) * 4096 + (col & 63));
       if (g != 0.f || ge != 0.f) {
-        const uint32_t col = vi << 3;
-        const float shift = part_max[static_cast<size_t>(col / BLOCK_N) * rows_pad + r] - l;  // log of the tile scale
-        const float cexp = __expf(shift);
-        const uint4 in = rowp[vi];
+        const uint4 in = *vecp;
         const uint32_t w[4] = {in.x, in.y, in.z, in.w};
         float f[8];
 #pragma unroll
@@ -205,9 +265,9 @@ __global__ void stash_to_dlogits_kernel(__nv_bfloat16* __restrict__ stash, int64
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float e = f[i];
-          const float p = cexp * e;
+          const float p = c * e;
           float d = -g * p;
-          if (ge != 0.f && e > 0.f) d -= ge * p * (shift + __logf(e) + h);
+          if (ge != 0.f && e > 0.f) d -= ge * p * (log_c + __logf(e) + h);
           f[i] = d;
         }
         const int64_t d = lab - static_cast<int64_t>(col);
@@ -221,7 +281,7 @@ __global__ void stash_to_dlogits_kernel(__nv_bfloat16* __restrict__ stash, int64
         out.z = pack_bf16x2(f[4], f[5]);
         out.w = pack_bf16x2(f[6], f[7]);
       }
-      rowp[vi] = out;
+      *vecp = out;
     }
   }
 }

@@ -90,20 +90,48 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
 }
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // clears the CTA-pair rank bit of a shared::cluster address
 
+// L2 eviction-priority policies for TMA loads (the encodings CUTLASS' TMA::CacheHintSm90 uses).
+constexpr uint64_t kEvictNormal = 0x1000000000000000ull;
+constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;  // streamed once: do not displace resident panels
+constexpr uint64_t kEvictLast = 0x14F0000000000000ull;   // re-read by every tile of the sweep: keep in L2
+
 // 2-D tile load, completes `bytes` on `bar`. kCta == 2: the completion lands on the pair leader's barrier.
 template <int kCta>
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int32_t c0, int32_t c1) {
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int32_t c0, int32_t c1,
+                                            uint64_t policy) {
   if constexpr (kCta == 1) {
     asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, "
+        "%4}], [%2], %5;"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
         : "memory");
   } else {
     asm volatile(
-        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, "
-        "%4}], [%2];"
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+        "[%0], [%1, {%3, %4}], [%2], %5;"
         ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0),
-        "r"(c1)
+        "r"(c1), "l"(policy)
+        : "memory");
+  }
+}
+
+// 4-D tile load (blocked operand layout [blk3][blk2][64][64]); same completion semantics as tma_load_2d.
+template <int kCta>
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int32_t c0, int32_t c1,
+                                            int32_t c2, int32_t c3, uint64_t policy) {
+  if constexpr (kCta == 1) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, "
+        "%4, %5, %6}], [%2], %7;"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+        "r"(c3), "l"(policy)
+        : "memory");
+  } else {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+        "[%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0),
+        "r"(c1), "r"(c2), "r"(c3), "l"(policy)
         : "memory");
   }
 }

@@ -49,7 +49,7 @@ def adv_close(got, want):
 
 # ================================================================================================ tcgen05 GEMM
 @pytest.mark.parametrize("cta", [1, 2])
-@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 1), (1, 0)])
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 1), (1, 0), (2, 1), (3, 1), (2, 0), (3, 0)])
 def test_debug_gemm_layouts(st, dev, cta, a_mn, b_mn):
     from spatialthinker_b200 import _lib
 
@@ -59,7 +59,14 @@ def test_debug_gemm_layouts(st, dev, cta, a_mn, b_mn):
     a = torch.randn(m, k, generator=g).to(torch.bfloat16)
     b = torch.randn(n, k, generator=g).to(torch.bfloat16)
     want = a.double() @ b.double().t()
-    a_d = (a.t().contiguous() if a_mn else a).to(dev)
+    def blocked(x):  # [r][c] -> [r/64][c/64][64][64], zero padded
+        r, c = x.shape
+        rp, cp = -(-r // 64) * 64, -(-c // 64) * 64
+        xp = torch.zeros(rp, cp, dtype=x.dtype)
+        xp[:r, :c] = x
+        return xp.view(rp // 64, 64, cp // 64, 64).permute(0, 2, 1, 3).contiguous()
+
+    a_d = {0: a, 1: a.t().contiguous(), 2: blocked(a), 3: blocked(a.t())}[a_mn].to(dev)
     b_d = (b.t().contiguous() if b_mn else b).to(dev)
     c = torch.full((m, n), 3.0, device=dev)
     _lib.check(lib.grpo_debug_gemm(a_d.data_ptr(), b_d.data_ptr(), c.data_ptr(), m, n, k, a_mn, b_mn, cta, 1,
@@ -370,6 +377,38 @@ def test_fused_grpo_loss_edge_cases(st, dev):
     with pytest.raises(NotImplementedError):
         st.fused_grpo_loss(x["hidden"].to(dev), x["weight"].to(dev), x["labels"].to(dev), lp, x["adv"].to(dev),
                            x["ref"].to(dev), x["mask"].to(dev), kl_penalty="full", kl_coef=0.1)
+
+
+def test_improbable_labels_and_garbage_padding(st, dev):
+    """The softmax is referenced to the label's own logit. Labels of very low probability (log p ~ -45) must still be
+    exact, and padded rows whose label is absurdly improbable must stay finite and contribute exactly nothing."""
+    bsz, tl, h, v = 4, 48, 128, 4096
+    g = torch.Generator().manual_seed(7)
+    hid = torch.randn(bsz, tl, h, generator=g).to(torch.bfloat16)
+    w = (0.45 * torch.randn(v, h, generator=g)).to(torch.bfloat16)  # logit std ~ 5, spread ~ +-20
+    z = hid.float() @ w.float().t()
+    labels = z.argmin(-1)  # the least likely token of every row
+    labels[:, ::3] = z.argmax(-1)[:, ::3]
+    want_lp, want_ent = O.lm_head_log_probs(hid, w, labels, 0.7, want_entropy=True)  # T = 0.7 widens the spread
+    assert -66 < float(want_lp.min()) < -40  # exact down to log p = -69 (kClampLog2), far below anything sampled
+    lp, ent = st.fused_lm_head_log_probs(hid.to(dev), w.to(dev), labels.to(dev), 0.7, want_entropy=True)
+    assert float((lp.cpu() - want_lp).abs().max()) < TOL_LOGP * 5  # |log p| up to 65: 1e-2 abs is 1.5e-4 relative here
+    assert float((ent.cpu() - want_ent).abs().max()) < TOL_LOGP
+    # garbage padding: rows 1 and 3 are fully masked and point at a token 200 nats below the row maximum
+    w2 = w.clone()
+    w2[7] = (-4.0 * hid[1, 0].float() / hid[1, 0].float().norm() * 10).to(torch.bfloat16)
+    mask = torch.ones(bsz, tl, dtype=torch.int64)
+    mask[1] = 0
+    mask[3] = 0
+    labels2 = labels.clone()
+    labels2[1] = 7
+    labels2[3] = 7
+    x = {"hidden": hid, "weight": w2, "labels": labels2, "mask": mask, "adv": torch.randn(bsz, 1, generator=g).expand(bsz, tl).contiguous()}
+    lp_ref, _ = O.lm_head_log_probs(hid, w2, labels2, 1.0)
+    x["old"] = O.perturbed_log_probs(lp_ref, seed=3)
+    x["ref"] = O.perturbed_log_probs(lp_ref, seed=4)
+    want, met = _check_fused_loss(st, dev, x, temperature=1.0)
+    assert bool(torch.isfinite(met["log_probs"]).all())
 
 
 def test_config_c1_full_head(st, dev):

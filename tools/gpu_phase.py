@@ -20,6 +20,8 @@ hid = torch.randn(rows, h, device=dev).to(torch.bfloat16)
 w = (0.02 * torch.randn(v, h, device=dev)).to(torch.bfloat16)
 labels = torch.randint(0, v, (rows,), device=dev)
 dlogp = torch.randn(rows, device=dev) / rows
+use_dent = os.environ.get("PHASE_DENT", "0") == "1"  # forces the stash -> dlogits transform path
+dent = torch.zeros(rows, device=dev) if use_dent else None
 dh = torch.empty(rows, h, device=dev, dtype=torch.bfloat16)
 dw = torch.zeros(v, h, device=dev, dtype=torch.float32)
 nbytes = lib.grpo_lmhead_bwd_workspace_bytes(rows, h, v)
@@ -27,7 +29,7 @@ ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
 
 
 def bwd():
-    _lib.check(lib.grpo_lmhead_bwd(hid.data_ptr(), w.data_ptr(), labels.data_ptr(), dlogp.data_ptr(), None, rows, h, v,
+    _lib.check(lib.grpo_lmhead_bwd(hid.data_ptr(), w.data_ptr(), labels.data_ptr(), dlogp.data_ptr(), dent.data_ptr() if use_dent else None, rows, h, v,
                                    1.0, dh.data_ptr(), dw.data_ptr(), ws.data_ptr(), nbytes, st), "bwd")
 
 
@@ -47,6 +49,6 @@ lib.grpo_profile_read(ms, cnt, 1)
 lib.grpo_profile_enable(0)
 tot = e0.elapsed_time(e1) / iters
 unit = 2.0 * rows * h * v
-knobs = {k: os.environ.get(k, "-") for k in ("GRPO_FWD_PANEL", "GRPO_SYNC_FWD", "GRPO_SYNC_DH", "GRPO_SYNC_DW", "GRPO_CTA_GROUP")}
+knobs = {k.replace("GRPO_", ""): os.environ[k] for k in sorted(os.environ) if k.startswith(("GRPO_", "PHASE_"))}
 parts = "  ".join(f"{n}={ms[i] / max(cnt[i], 1):.3f}" for i, n in enumerate(_lib.PHASE_NAMES))
 print(f"{knobs} total={tot:.3f} ms ({3 * unit / tot / 1e9:.0f} TF alg) | {parts}")

@@ -1,10 +1,8 @@
-run() { env "$@" python tools/gpu_phase.py 3584 9472 6 2>&1 | tail -1; }
-run GRPO_SYNC_FWD=0 GRPO_SYNC_DH=0 GRPO_SYNC_DW=0 GRPO_FWD_PANEL=37
-run GRPO_SYNC_FWD=0 GRPO_SYNC_DH=0 GRPO_SYNC_DW=0 GRPO_FWD_PANEL=19
-run GRPO_SYNC_FWD=448 GRPO_SYNC_DH=0 GRPO_SYNC_DW=0 GRPO_FWD_PANEL=19
-run GRPO_SYNC_FWD=0 GRPO_SYNC_DH=128 GRPO_SYNC_DW=0 GRPO_FWD_PANEL=37
-run GRPO_SYNC_FWD=0 GRPO_SYNC_DH=512 GRPO_SYNC_DW=0 GRPO_FWD_PANEL=37
-run GRPO_SYNC_FWD=0 GRPO_SYNC_DH=2374 GRPO_SYNC_DW=0 GRPO_FWD_PANEL=37
-run GRPO_SYNC_FWD=0 GRPO_SYNC_DH=0 GRPO_SYNC_DW=148 GRPO_FWD_PANEL=37
-run GRPO_SYNC_FWD=0 GRPO_SYNC_DH=0 GRPO_SYNC_DW=592 GRPO_FWD_PANEL=37
-run GRPO_SYNC_FWD=0 GRPO_SYNC_DH=0 GRPO_SYNC_DW=37 GRPO_FWD_PANEL=37
+run() { env "$@" python tools/gpu_phase.py 3584 9472 8 2>&1 | tail -1; }
+for rep in 1 2; do
+run PHASE_DENT=0 GRPO_L2_HINTS=1
+run PHASE_DENT=1 GRPO_L2_HINTS=1
+run PHASE_DENT=0 GRPO_L2_HINTS=0
+run PHASE_DENT=1 GRPO_L2_HINTS=0
+done
+nvidia-smi --query-gpu=temperature.gpu,power.draw,clocks.sm --format=csv
