@@ -21,7 +21,6 @@ namespace grpo {
 constexpr int kBlockM = 128;  // accumulator rows per CTA (= TMEM lanes)
 constexpr int kBlockK = 64;   // 64 bf16 = one 128-byte swizzle row
 constexpr int kUmmaK = 16;
-constexpr int kNumThreads = 256;
 constexpr int kEpiWarp0 = 4;
 constexpr int kNumEpiThreads = 128;
 
@@ -88,33 +87,48 @@ __device__ __forceinline__ void decode_tile(const TileSched& s, uint32_t t, uint
   }
 }
 
-// What an epilogue sees for one accumulator tile.
+// What an epilogue sees for one 128 x BLOCK_N accumulator.
 struct EpiCtx {
-  uint32_t m_blk, n_blk;
-  uint32_t row_in_tile;  // 0 .. 128*kCta-1 : this thread's accumulator row inside the (pair) tile
-  uint32_t warp, lane;   // epilogue warp 0..3, lane
-  uint32_t tmem_acc;     // TMEM address of this warp's lanes, column 0 of the accumulator stage
+  uint32_t row;       // global output row owned by this thread (TMEM lane)
+  uint32_t n_blk;     // column block index
+  uint32_t col0;      // first global column of the accumulator
+  uint32_t warp, lane;
+  uint32_t tmem_acc;  // TMEM address of this warp's lanes, column 0 of the accumulator
 };
 
-template <int kCta, int BLOCK_N, int kStages>
+// kSub = number of 128-row accumulators a CTA computes per tile (its share of the tile is 128 * kSub rows):
+//   kSub == 1: 128 x BLOCK_N per CTA; the two TMEM accumulator slots double-buffer consecutive tiles, so the epilogue
+//              of tile t fully overlaps the MMAs of tile t+1. Shared-memory traffic per MMA cycle is (128 + BLOCK_N /
+//              kCta) operand rows in plus the MMA's own operand reads - on a CTA pair exactly the 128 B/clk the SM can
+//              move, which caps the tensor pipe near 84 % (measured, profiles/).
+//   kSub == 2: 256 x BLOCK_N per CTA; both TMEM slots are live at once, every B stage is used by two MMAs, operand
+//              traffic per MMA cycle drops by a quarter (the tile shape cuBLAS picks) and the main loop can run the
+//              tensor pipe flat out; the price is that the epilogue (two warpgroups, one per accumulator) no longer
+//              hides behind the next tile's MMAs.
+template <int kCta, int kSub, int BLOCK_N, int kStages>
 struct GemmCfg {
+  static constexpr int kRowsPerCta = kBlockM * kSub;
+  static constexpr int kTileRows = kRowsPerCta * kCta;
   static constexpr int kLoadN = BLOCK_N / kCta;  // B columns each CTA loads
-  static constexpr int kABytes = kBlockM * kBlockK * 2;
+  static constexpr int kABytes = kRowsPerCta * kBlockK * 2;
   static constexpr int kBBytes = kLoadN * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kRingBytes = kStages * kStageBytes;
   static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
   static constexpr int kTmemCols = 2 * BLOCK_N;
+  static constexpr int kEpiWarps = 4 * kSub;
+  static constexpr int kThreads = 128 + 32 * kEpiWarps;
+  static_assert(kSub == 1 || kSub == 2, "one or two accumulators per CTA");
   static_assert(kTmemCols == 512 || kTmemCols == 256 || kTmemCols == 128 || kTmemCols == 64, "TMEM columns");
   static_assert(BLOCK_N % 16 == 0 && BLOCK_N <= 256, "UMMA N");
   static constexpr size_t smem_bytes(int epi_bytes) { return 1024 + kRingBytes + epi_bytes + kBarBytes; }
 };
 
-template <int kCta, int BLOCK_N, int kStages, int kAMode, bool kBMn, class Epi>
-__global__ void __launch_bounds__(kNumThreads, 1)
+template <int kCta, int kSub, int BLOCK_N, int kStages, int kAMode, bool kBMn, class Epi>
+__global__ void __launch_bounds__(128 + 128 * kSub, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
             const TileSched sched, const typename Epi::Params ep) {
-  using Cfg = GemmCfg<kCta, BLOCK_N, kStages>;
+  using Cfg = GemmCfg<kCta, kSub, BLOCK_N, kStages>;
   constexpr bool kAMn = (kAMode & 1) != 0;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -144,7 +158,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);                        // one tcgen05.commit
-      mbar_init(&tmem_empty[i], kCta * kNumEpiThreads);  // every epilogue thread of the pair, on the leader
+      mbar_init(&tmem_empty[i], kCta * kNumEpiThreads);  // the warpgroup draining this slot, in every CTA of the pair
     }
     fence_mbar_init();
   }
@@ -170,7 +184,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       for (uint32_t t = first_tile; t < num_tiles; t += tile_step) {
         uint32_t m_blk, n_blk;
         decode_tile(sched, t, m_blk, n_blk);
-        const int32_t m0 = static_cast<int32_t>(m_blk * (kBlockM * kCta) + rank * kBlockM);
+        const int32_t m0 = static_cast<int32_t>(m_blk * Cfg::kTileRows + rank * Cfg::kRowsPerCta);
         const int32_t n0 = static_cast<int32_t>(n_blk * BLOCK_N + rank * Cfg::kLoadN);
         for (uint32_t kb = 0; kb < sched.k_blocks; ++kb, ++progress) {
           if (do_sync && progress != 0 && progress % sched.sync_period == 0)
@@ -183,11 +197,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             tma_load_2d<kCta>(&tmap_a, &full_bar[stage], sa, k0, m0, sched.hint_a);
           } else if constexpr (kAMode == A_MN_MAJOR) {
 #pragma unroll
-            for (int i = 0; i < kBlockM / 64; ++i)
+            for (int i = 0; i < Cfg::kRowsPerCta / 64; ++i)
               tma_load_2d<kCta>(&tmap_a, &full_bar[stage], sa + i * (kBlockK * 128), m0 + i * 64, k0, sched.hint_a);
-          } else if constexpr (kAMode == A_BLOCKED_K) {  // box (64, 64, 1 K-block, 2 row blocks)
+          } else if constexpr (kAMode == A_BLOCKED_K) {  // box (64, 64, 1 K-block, kRowsPerCta / 64 row blocks)
             tma_load_4d<kCta>(&tmap_a, &full_bar[stage], sa, 0, 0, static_cast<int32_t>(kb), m0 >> 6, sched.hint_a);
-          } else {  // A_BLOCKED_MN: box (64, 64, 2 row blocks, 1 K-block)
+          } else {  // A_BLOCKED_MN: box (64, 64, kRowsPerCta / 64 row blocks, 1 K-block)
             tma_load_4d<kCta>(&tmap_a, &full_bar[stage], sa, 0, 0, m0 >> 6, static_cast<int32_t>(kb), sched.hint_a);
           }
           if constexpr (!kBMn) {
@@ -215,12 +229,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       constexpr uint32_t idesc = make_idesc_bf16(kBlockM * kCta, BLOCK_N, kAMn, kBMn);
       constexpr uint32_t a_lbo = kAMn ? kBlockK * 128 : 0, b_lbo = kBMn ? kBlockK * 128 : 0;
       constexpr uint32_t a_kstep = kAMn ? kUmmaK * 128 : kUmmaK * 2, b_kstep = kBMn ? kUmmaK * 128 : kUmmaK * 2;
+      constexpr uint32_t a_sub = kBlockM * 128;  // 128 rows further on: 16 KB in either majorness (two 8 KB MN atoms)
       uint32_t stage = 0, phase = 0, it = 0;
       for (uint32_t t = first_tile; t < num_tiles; t += tile_step, ++it) {
-        const uint32_t as = it & 1, ap = (it >> 1) & 1;
-        mbar_wait(&tmem_empty[as], ap ^ 1);
+        // accumulator slots: kSub == 1 alternates them tile by tile, kSub == 2 uses both for every tile
+        const uint32_t slot0 = (kSub == 1) ? (it & 1) : 0u;
+        const uint32_t ap = (kSub == 1) ? ((it >> 1) & 1) : (it & 1);
+        mbar_wait(&tmem_empty[slot0], ap ^ 1);
+        if (kSub == 2) mbar_wait(&tmem_empty[1], ap ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * BLOCK_N;
         for (uint32_t kb = 0; kb < sched.k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -228,39 +245,54 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           const uint32_t b_addr = smem_u32(smem_b + stage * Cfg::kBBytes);
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-            const uint64_t da = make_smem_desc(a_addr + k * a_kstep, 1024, a_lbo);
             const uint64_t db = make_smem_desc(b_addr + k * b_kstep, 1024, b_lbo);
-            umma_bf16<kCta>(d_tmem, da, db, idesc, (kb | k) != 0);
+#pragma unroll
+            for (int sub = 0; sub < kSub; ++sub) {
+              const uint64_t da = make_smem_desc(a_addr + sub * a_sub + k * a_kstep, 1024, a_lbo);
+              umma_bf16<kCta>(tmem_base + (slot0 + sub) * BLOCK_N, da, db, idesc, (kb | k) != 0);
+            }
           }
           umma_commit<kCta>(&empty_bar[stage]);  // frees the smem slot (both CTAs) when these MMAs retire
-          if (kb + 1 == sched.k_blocks) umma_commit<kCta>(&tmem_full[as]);
+          if (kb + 1 == sched.k_blocks) {
+            umma_commit<kCta>(&tmem_full[slot0]);
+            if (kSub == 2) umma_commit<kCta>(&tmem_full[1]);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
       // the peer's last remote arrivals must land before this CTA's barriers go away
       if (kCta == 2 && it > 0) {
         const uint32_t last = it - 1;
-        mbar_wait(&tmem_empty[last & 1], (last >> 1) & 1);
+        if (kSub == 1) {
+          mbar_wait(&tmem_empty[last & 1], (last >> 1) & 1);
+        } else {
+          mbar_wait(&tmem_empty[0], last & 1);
+          mbar_wait(&tmem_empty[1], last & 1);
+        }
       }
     }
   } else if (warp >= kEpiWarp0) {
-    // ------------------------------------------------------------------ epilogue
+    // ------------------------------------------------------------------ epilogue: one warpgroup per accumulator
     const uint32_t ew = warp - kEpiWarp0;
+    const uint32_t grp = ew >> 2, quad = ew & 3;  // warp (4 + ew) may touch TMEM lanes 32 * (ew % 4) .. +31
     uint32_t it = 0;
     for (uint32_t t = first_tile; t < num_tiles; t += tile_step, ++it) {
-      const uint32_t as = it & 1, ap = (it >> 1) & 1;
+      const uint32_t slot = (kSub == 1) ? (it & 1) : grp;
+      const uint32_t ap = (kSub == 1) ? ((it >> 1) & 1) : (it & 1);
       EpiCtx c;
-      decode_tile(sched, t, c.m_blk, c.n_blk);
-      c.warp = ew;
+      uint32_t m_blk;
+      decode_tile(sched, t, m_blk, c.n_blk);
+      c.warp = quad;
       c.lane = lane;
-      c.row_in_tile = rank * kBlockM + ew * 32 + lane;
-      c.tmem_acc = tmem_base + as * BLOCK_N + ((ew * 32u) << 16);
-      mbar_wait(&tmem_full[as], ap);
+      c.row = m_blk * Cfg::kTileRows + rank * Cfg::kRowsPerCta + grp * kBlockM + quad * 32 + lane;
+      c.col0 = c.n_blk * BLOCK_N;
+      c.tmem_acc = tmem_base + slot * BLOCK_N + ((quad * 32u) << 16);
+      mbar_wait(&tmem_full[slot], ap);
       tc_fence_after();
       Epi::run(ep, c, smem_epi);  // returns with all of its TMEM loads complete
       tc_fence_before();
-      if (leader) mbar_arrive(&tmem_empty[as]);
-      else mbar_arrive_cluster(&tmem_empty[as], 0);
+      if (leader) mbar_arrive(&tmem_empty[slot]);
+      else mbar_arrive_cluster(&tmem_empty[slot], 0);
     }
   }
 
@@ -284,8 +316,7 @@ struct EpiF32 {
   };
   static constexpr int kSmemBytes = 0;
   __device__ static void run(const Params& p, const EpiCtx& c, uint8_t*) {
-    const uint32_t row = c.m_blk * (kBlockM * kCta) + c.row_in_tile;
-    const uint32_t col0 = c.n_blk * BLOCK_N;
+    const uint32_t row = c.row, col0 = c.col0;
     float* out = p.c + static_cast<int64_t>(row) * p.ldc + col0;
 #pragma unroll 1
     for (int g = 0; g < BLOCK_N / 32; ++g) {
@@ -326,8 +357,7 @@ struct EpiBF16 {
   };
   static constexpr int kSmemBytes = 0;
   __device__ static void run(const Params& p, const EpiCtx& c, uint8_t*) {
-    const uint32_t row = c.m_blk * (kBlockM * kCta) + c.row_in_tile;
-    const uint32_t col0 = c.n_blk * BLOCK_N;
+    const uint32_t row = c.row, col0 = c.col0;
     const bool row_ok = row < p.m;
     __nv_bfloat16* out = p.c + static_cast<int64_t>(row) * p.ldc + col0;
     const float sc = (row_ok && p.row_scale) ? p.row_scale[row] : 1.f;

@@ -160,15 +160,18 @@ static int make_operand_tmap(CUtensorMap* map, const void* base, uint64_t rows, 
 // override them for experiments.
 struct Knobs {
   int cta_group = 2;   // 2: one 256 x 256 tile per CTA pair (cta_group::2); 1: 128 x 256 per CTA (debug)
-  int fwd_panel = 19;  // row blocks (of 256) of the logits GEMM kept L2-resident under the vocab sweep (19 x 256 x H bf16)
-  // progress-barrier periods in K-blocks (0 = off). Measured on B200 (profiles/r1_knobs.md): the barrier cuts DRAM
-  // traffic but its stalls cost more tensor-pipe time than the traffic costs clock - default free-running.
-  int sync_fwd = 0, sync_dh = 0, sync_dw = 0;
+  int ksub = 2;        // 128-row accumulators per CTA and tile: 2 = wide 512 x 256 pair tile, 1 = 256 x 256 double-buffered
+  int fwd_panel = 4864;  // rows of hidden the logits GEMM keeps L2-resident under one vocab sweep (35 MB at H = 3584)
+  // progress-window periods in K-blocks (0 = free running). Persistent CTA pairs drift apart, and tiles that share an
+  // operand panel then each stream their own copy from HBM (dHidden GEMM: 32 GB instead of 11 GB per chunk, measured
+  // with ncu). Bounding the drift to two short windows keeps the shared panels L2-hot; with the wide tile (ksub = 2)
+  // that is worth 6-7 % end to end (profiles/r1_knobs.md). Values: interleaved A/B sweep on B200.
+  int sync_fwd = 28, sync_dh = 8, sync_dw = 8;
   // L2 eviction priorities on the TMA loads, bit 0: logits GEMM (hidden panel evict-last, W evict-first), bit 1: dW GEMM
   // (scaled hidden evict-last, stash evict-first). Measured (profiles/r1_knobs.md): both cost 2-3 % - default off.
   int l2_hints = 0;
   int dh_m_fast = 0;   // tile order of the dHidden GEMM (experiment)
-  int chunk_rows = 9472;  // rows per chunk of the pipeline (multiple of 256)
+  int chunk_rows = 0;  // rows per chunk of the pipeline (0: 37 row tiles, see default_chunk_rows)
 };
 static Knobs g_knobs;
 static std::once_flag g_knobs_once;
@@ -179,6 +182,7 @@ static int env_int(const char* name, int dflt) {
 static void init_knobs() {
   std::call_once(g_knobs_once, [] {
     g_knobs.cta_group = env_int("GRPO_CTA_GROUP", g_knobs.cta_group) == 1 ? 1 : 2;
+    g_knobs.ksub = env_int("GRPO_KSUB", g_knobs.ksub) == 1 ? 1 : 2;
     g_knobs.fwd_panel = env_int("GRPO_FWD_PANEL", g_knobs.fwd_panel);
     g_knobs.sync_fwd = env_int("GRPO_SYNC_FWD", g_knobs.sync_fwd);
     g_knobs.sync_dh = env_int("GRPO_SYNC_DH", g_knobs.sync_dh);
@@ -210,11 +214,11 @@ static int get_dev(DevInfo* out) {
 }
 
 // ------------------------------------------------------------------------------------------ GEMM launch
-template <int kCta, int BLOCK_N, int kStages, int kAMode, bool kBMn, class Epi>
+template <int kCta, int kSub, int BLOCK_N, int kStages, int kAMode, bool kBMn, class Epi>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const TileSched& sched,
                        const typename Epi::Params& ep, int sms, cudaStream_t stream) {
-  using Cfg = GemmCfg<kCta, BLOCK_N, kStages>;
-  auto kern = gemm_kernel<kCta, BLOCK_N, kStages, kAMode, kBMn, Epi>;
+  using Cfg = GemmCfg<kCta, kSub, BLOCK_N, kStages>;
+  auto kern = gemm_kernel<kCta, kSub, BLOCK_N, kStages, kAMode, kBMn, Epi>;
   const size_t smem = Cfg::smem_bytes(Epi::kSmemBytes);
   GRPO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   const uint32_t tiles = sched.m_blocks * sched.n_blocks;
@@ -223,7 +227,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const TileS
   if (groups > tiles) groups = tiles;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(groups * kCta);
-  cfg.blockDim = dim3(kNumThreads);
+  cfg.blockDim = dim3(Cfg::kThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -239,32 +243,39 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const TileS
 }
 
 constexpr int kBlockN = 256;
-constexpr int kStages1 = 4;  // 48 KB / stage
-constexpr int kStages2 = 6;  // 32 KB / stage (each CTA of the pair loads half of B)
+// smem ring depth per configuration (stage = A rows + B rows, 128 B each):
+constexpr int kStages11 = 4;  // 1 CTA,  128 + 256 rows = 48 KB
+constexpr int kStages21 = 6;  // pair,   128 + 128 rows = 32 KB
+constexpr int kStages22 = 4;  // pair,   256 + 128 rows = 48 KB   (wide tile)
 
 static inline uint32_t cdiv(uint64_t a, uint64_t b) { return static_cast<uint32_t>((a + b - 1) / b); }
 
-// Rows per chunk of the chunked lm_head pipeline: 37 row-blocks of 256. With 74 CTA pairs, 37 x (H/256) output tiles
-// of the dHidden GEMM is a whole number of waves for H = 2048 (4) and H = 3584 (7); the chunk's exp-stash is
-// 9472 x V bf16 (2.9 GB at V = 151936).
-constexpr int64_t kChunkRowsDefault = 9472;
+// Tile geometry for a knob setting: rows of A per CTA-group tile.
+static inline int tile_rows(int cta_group, int ksub) { return kBlockM * cta_group * (cta_group == 2 ? ksub : 1); }
+
+// Rows per chunk of the chunked lm_head pipeline. With 74 CTA pairs the dHidden GEMM's (rows / tile_rows) x (H / 256)
+// output tiles should be a whole number of waves: 37 row blocks give 4 / 7 waves for H = 2048 / 3584. That is 9472
+// rows with 256-row tiles (exp-stash 2.9 GB at V = 151936) and 18944 rows with the wide 512-row tiles (5.8 GB).
+static inline int64_t default_chunk_rows(int cta_group, int ksub) { return 37ll * tile_rows(cta_group == 1 ? 2 : cta_group, ksub); }
 
 template <int kAMode, bool kBMn, class Epi1, class Epi2>
-static int launch_gemm_any(int cta_group, const void* a, uint64_t a_rows, uint64_t a_pitch, const void* b,
+static int launch_gemm_any(const DevInfo& dev, const void* a, uint64_t a_rows, uint64_t a_pitch, const void* b,
                            uint64_t b_rows, uint64_t b_pitch, uint64_t k, TileSched sched,
-                           const typename Epi1::Params& ep1, const typename Epi2::Params& ep2, int sms,
-                           cudaStream_t stream) {
+                           const typename Epi1::Params& ep1, const typename Epi2::Params& ep2, cudaStream_t stream) {
+  const int cta_group = dev.cta_group, ksub = (cta_group == 2) ? dev.ksub : 1;
+  const int trows = tile_rows(cta_group, ksub);
   CUtensorMap ta, tb;
-  GRPO_TRY(make_operand_tmap(&ta, a, a_rows, k, a_pitch, kAMode, kBlockM));
+  GRPO_TRY(make_operand_tmap(&ta, a, a_rows, k, a_pitch, kAMode, trows / cta_group));
   GRPO_TRY(make_operand_tmap(&tb, b, b_rows, k, b_pitch, kBMn ? A_MN_MAJOR : A_K_MAJOR, kBlockN / cta_group));
-  sched.m_blocks = cdiv(a_rows, kBlockM * cta_group);
+  sched.m_blocks = cdiv(a_rows, trows);
   sched.n_blocks = cdiv(b_rows, kBlockN);
   sched.k_blocks = cdiv(k, kBlockK);
   if (sched.panel_m == 0 || sched.panel_m > sched.m_blocks) sched.panel_m = sched.m_blocks;
   if (sched.hint_a == 0) sched.hint_a = kEvictNormal;
   if (sched.hint_b == 0) sched.hint_b = kEvictNormal;
-  if (cta_group == 1) return launch_gemm<1, kBlockN, kStages1, kAMode, kBMn, Epi1>(ta, tb, sched, ep1, sms, stream);
-  return launch_gemm<2, kBlockN, kStages2, kAMode, kBMn, Epi2>(ta, tb, sched, ep2, sms, stream);
+  if (cta_group == 1) return launch_gemm<1, 1, kBlockN, kStages11, kAMode, kBMn, Epi1>(ta, tb, sched, ep1, dev.sms, stream);
+  if (ksub == 1) return launch_gemm<2, 1, kBlockN, kStages21, kAMode, kBMn, Epi2>(ta, tb, sched, ep2, dev.sms, stream);
+  return launch_gemm<2, 2, kBlockN, kStages22, kAMode, kBMn, Epi2>(ta, tb, sched, ep2, dev.sms, stream);
 }
 
 // ------------------------------------------------------------------------------------------ workspace
@@ -289,10 +300,10 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 static Workspace carve(void* base, int64_t rows, int64_t hdim, int64_t vocab, bool with_stash) {
   Workspace w;
   init_knobs();
-  const int64_t chunk_cap = g_knobs.chunk_rows > 0 ? g_knobs.chunk_rows : kChunkRowsDefault;
+  const int64_t chunk_cap = g_knobs.chunk_rows > 0 ? g_knobs.chunk_rows : default_chunk_rows(g_knobs.cta_group, g_knobs.ksub);
   w.chunk_rows = rows < chunk_cap ? rows : chunk_cap;
   if (w.chunk_rows < 1) w.chunk_rows = 1;
-  w.rows_pad = static_cast<int64_t>(align_up(static_cast<size_t>(w.chunk_rows), 256));
+  w.rows_pad = static_cast<int64_t>(align_up(static_cast<size_t>(w.chunk_rows), 512));
   w.n_tiles = (vocab + kBlockN - 1) / kBlockN;
   size_t off = 0;
   uint8_t* p = static_cast<uint8_t*>(base);
@@ -363,7 +374,11 @@ static int chunk_forward(const DevInfo& dev, const Workspace& w, const __nv_bflo
   memcpy(&p2, &p1, sizeof(p1));
   TileSched s{};
   s.m_fast = 1;  // walk the row blocks of a panel under one vocab tile: the hidden panel stays in L2, W streams by
-  s.panel_m = static_cast<uint32_t>(dev.fwd_panel * (dev.cta_group == 1 ? 2 : 1));  // counted in blocks of 128 * cta_group
+  {
+    const int trows = tile_rows(dev.cta_group, dev.cta_group == 2 ? dev.ksub : 1);
+    s.panel_m = static_cast<uint32_t>((dev.fwd_panel + trows / 2) / trows);
+    if (s.panel_m == 0) s.panel_m = 1;
+  }
   s.sync_period = static_cast<uint32_t>(dev.sync_fwd);
   s.sync_ctr = w.sync;
   if (dev.l2_hints & 1) {  // the hidden panel is re-read under every vocab tile; a W tile is dead after one panel pass
@@ -374,7 +389,7 @@ static int chunk_forward(const DevInfo& dev, const Workspace& w, const __nv_bflo
   {
     PhaseScope ps(PH_LOGITS_GEMM, stream);
     GRPO_TRY((launch_gemm_any<A_K_MAJOR, false, EpiSoftmax<1, kBlockN>, EpiSoftmax<2, kBlockN>>(
-        dev.cta_group, hidden + r0 * h, n, h, weight, v, h, h, s, p1, p2, dev.sms, stream)));
+        dev, hidden + r0 * h, n, h, weight, v, h, h, s, p1, p2, stream)));
   }
   PhaseScope ps(PH_ROW_STATS, stream);
   combine_rows_kernel<<<cdiv(n, 32), dim3(32, 8), 0, stream>>>(
@@ -420,7 +435,7 @@ static int chunk_backward(const DevInfo& dev, const Workspace& w, const __nv_bfl
     s.sync_period = static_cast<uint32_t>(dev.sync_dh);
     s.sync_ctr = w.sync + 1;
     GRPO_TRY((launch_gemm_any<A_BLOCKED_K, true, EpiBF16<1, kBlockN>, EpiBF16<2, kBlockN>>(
-        dev.cta_group, w.stash, n, w.stash_vb, weight, h, h, v, s, p1, p2, dev.sms, stream)));
+        dev, w.stash, n, w.stash_vb, weight, h, h, v, s, p1, p2, stream)));
   }
   {  // dW[v][h] += E^T[v][n] . hd[n][h]    A = stash read transposed (MN-major), B = (scaled) hidden read transposed
     PhaseScope ps(PH_DW_GEMM, stream);
@@ -436,7 +451,7 @@ static int chunk_backward(const DevInfo& dev, const Workspace& w, const __nv_bfl
     }
     const __nv_bfloat16* b_op = factorised ? w.hd_scaled : hidden + r0 * h;
     GRPO_TRY((launch_gemm_any<A_BLOCKED_MN, true, EpiF32<1, kBlockN>, EpiF32<2, kBlockN>>(
-        dev.cta_group, w.stash, v, w.stash_vb, b_op, h, h, n, s, p1, p2, dev.sms, stream)));
+        dev, w.stash, v, w.stash_vb, b_op, h, h, n, s, p1, p2, stream)));
   }
   return 0;
 }
@@ -473,13 +488,14 @@ int grpo_set_option(const char* name, int value) {
   init_knobs();
   if (!name) return fail(GRPO_ERR_ARG, "null option name");
   if (!strcmp(name, "cta_group")) g_knobs.cta_group = value == 1 ? 1 : 2;
-  else if (!strcmp(name, "fwd_panel")) g_knobs.fwd_panel = value > 0 ? value : 19;
+  else if (!strcmp(name, "ksub")) g_knobs.ksub = value == 1 ? 1 : 2;
+  else if (!strcmp(name, "fwd_panel")) g_knobs.fwd_panel = value > 0 ? value : 4864;
   else if (!strcmp(name, "sync_fwd")) g_knobs.sync_fwd = value;
   else if (!strcmp(name, "sync_dh")) g_knobs.sync_dh = value;
   else if (!strcmp(name, "sync_dw")) g_knobs.sync_dw = value;
   else if (!strcmp(name, "l2_hints")) g_knobs.l2_hints = value;
   else if (!strcmp(name, "dh_m_fast")) g_knobs.dh_m_fast = value;
-  else if (!strcmp(name, "chunk_rows")) g_knobs.chunk_rows = value > 0 ? (value + 255) / 256 * 256 : 9472;
+  else if (!strcmp(name, "chunk_rows")) g_knobs.chunk_rows = value > 0 ? (value + 511) / 512 * 512 : 0;
   else return fail(GRPO_ERR_ARG, "unknown option '%s'", name);
   return 0;
 }
@@ -823,6 +839,7 @@ int grpo_debug_gemm(const void* a, const void* b, float* c, int64_t m, int64_t n
   if (cta_group != 1 && cta_group != 2) return fail(GRPO_ERR_ARG, "cta_group must be 1 or 2");
   DevInfo dev;
   GRPO_TRY(get_dev(&dev));
+  dev.cta_group = cta_group;  // explicit for the debug entry; the tile shape (ksub) follows the process-wide knob
   EpiF32<1, kBlockN>::Params p1{c, n, static_cast<uint32_t>(m), static_cast<uint32_t>(n),
                                 static_cast<uint32_t>(accumulate != 0)};
   EpiF32<2, kBlockN>::Params p2{c, n, static_cast<uint32_t>(m), static_cast<uint32_t>(n),
@@ -834,8 +851,7 @@ int grpo_debug_gemm(const void* a, const void* b, float* c, int64_t m, int64_t n
   const uint64_t b_pitch = b_mn_major ? n : k;
   using E1 = EpiF32<1, kBlockN>;
   using E2 = EpiF32<2, kBlockN>;
-#define GRPO_DBG(AM, BM) \
-  return launch_gemm_any<AM, BM, E1, E2>(cta_group, a, m, a_pitch, b, n, b_pitch, k, s, p1, p2, dev.sms, stream)
+#define GRPO_DBG(AM, BM) return launch_gemm_any<AM, BM, E1, E2>(dev, a, m, a_pitch, b, n, b_pitch, k, s, p1, p2, stream)
   switch (a_mn_major * 2 + (b_mn_major ? 1 : 0)) {
     case 0: GRPO_DBG(A_K_MAJOR, false);
     case 1: GRPO_DBG(A_K_MAJOR, true);

@@ -67,9 +67,8 @@ struct EpiSoftmax {
   static constexpr int kSmemBytes = 0;
 
   __device__ static void run(const Params& p, const EpiCtx& c, uint8_t*) {
-    const uint32_t row = c.m_blk * (kBlockM * kCta) + c.row_in_tile;
+    const uint32_t row = c.row, col0 = c.col0;
     const bool row_ok = row < p.rows;
-    const uint32_t col0 = c.n_blk * BLOCK_N;
     const uint32_t ncols = min(static_cast<uint32_t>(BLOCK_N), p.vocab - col0);
     const uint32_t ngroups = (ncols + 31) >> 5;  // column groups of 32 that hold at least one real vocabulary entry
     const float c1 = p.scale * kLog2e;

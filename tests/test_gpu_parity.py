@@ -394,17 +394,23 @@ def test_improbable_labels_and_garbage_padding(st, dev):
     lp, ent = st.fused_lm_head_log_probs(hid.to(dev), w.to(dev), labels.to(dev), 0.7, want_entropy=True)
     assert float((lp.cpu() - want_lp).abs().max()) < TOL_LOGP * 5  # |log p| up to 65: 1e-2 abs is 1.5e-4 relative here
     assert float((ent.cpu() - want_ent).abs().max()) < TOL_LOGP
-    # garbage padding: rows 1 and 3 are fully masked and point at a token 200 nats below the row maximum
+    # garbage padding: sequences 1 and 3 are fully masked and point at a token that is > 100 nats below the row maximum
+    # at position 0 (the clamp binds there); the valid sequences keep ordinary labels
     w2 = w.clone()
-    w2[7] = (-4.0 * hid[1, 0].float() / hid[1, 0].float().norm() * 10).to(torch.bfloat16)
+    w2[7] = (-8.0 * hid[1, 0].float() / hid[1, 0].float().norm() * 1.0).to(torch.bfloat16)
+    w2[7] += (-8.0 * hid[3, 0].float() / hid[3, 0].float().norm()).to(torch.bfloat16)
+    z2 = hid.float() @ w2.float().t()
+    assert float(z2[1, 0].max() - z2[1, 0, 7]) > 80
     mask = torch.ones(bsz, tl, dtype=torch.int64)
     mask[1] = 0
     mask[3] = 0
-    labels2 = labels.clone()
+    labels2 = z2.argmax(-1)
+    labels2[:, 1::2] = torch.randint(0, v, (bsz, tl // 2), generator=g)
     labels2[1] = 7
     labels2[3] = 7
     x = {"hidden": hid, "weight": w2, "labels": labels2, "mask": mask, "adv": torch.randn(bsz, 1, generator=g).expand(bsz, tl).contiguous()}
     lp_ref, _ = O.lm_head_log_probs(hid, w2, labels2, 1.0)
+    assert float(lp_ref[mask.bool()].min()) > -60
     x["old"] = O.perturbed_log_probs(lp_ref, seed=3)
     x["ref"] = O.perturbed_log_probs(lp_ref, seed=4)
     want, met = _check_fused_loss(st, dev, x, temperature=1.0)

@@ -38,12 +38,13 @@ nbytes = 0
 for spec in args.variants:  # the workspace must fit the largest chunk setting among the variants
     for kv in filter(None, spec.split(",")):
         k, val = kv.split("=")
-        if k == "chunk_rows":
-            lib.grpo_set_option(b"chunk_rows", int(val))
+        if k in ("chunk_rows", "ksub"):
+            lib.grpo_set_option(k.encode(), int(val))
     nbytes = max(nbytes, lib.grpo_lmhead_bwd_workspace_bytes(rows, h, v))
-    lib.grpo_set_option(b"chunk_rows", 9472)
+    lib.grpo_set_option(b"chunk_rows", 0)
+    lib.grpo_set_option(b"ksub", 2)
 ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-DEFAULTS = {"cta_group": 2, "fwd_panel": 19, "sync_fwd": 0, "sync_dh": 0, "sync_dw": 0, "l2_hints": 0, "dh_m_fast": 0, "chunk_rows": 9472}
+DEFAULTS = {"cta_group": 2, "fwd_panel": 4864, "sync_fwd": 28, "sync_dh": 8, "sync_dw": 8, "l2_hints": 0, "dh_m_fast": 0, "chunk_rows": 0, "ksub": 2}
 
 
 def apply(spec):
