@@ -40,7 +40,7 @@ def test_workspace_queries_are_host_only(lib):
     assert 0 < small < big
     # the stash never exceeds one chunk of rows, whatever the micro-batch size
     assert big == lib.grpo_fused_loss_workspace_bytes(1 << 22, 3584, 151936)
-    assert big < 3.2e9
+    assert big < 6.5e9  # one chunk of 18944 rows: 5.8 GB of exp-stash + 0.14 GB scaled hidden + partial sums
 
 
 def test_sass_is_blackwell_native():
