@@ -235,28 +235,29 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         // accumulator slots: kSub == 1 alternates them tile by tile, kSub == 2 uses both for every tile
         const uint32_t slot0 = (kSub == 1) ? (it & 1) : 0u;
         const uint32_t ap = (kSub == 1) ? ((it >> 1) & 1) : (it & 1);
-        mbar_wait(&tmem_empty[slot0], ap ^ 1);
-        if (kSub == 2) mbar_wait(&tmem_empty[1], ap ^ 1);
-        tc_fence_after();
         for (uint32_t kb = 0; kb < sched.k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem_a + stage * Cfg::kABytes);
           const uint32_t b_addr = smem_u32(smem_b + stage * Cfg::kBBytes);
+          const bool last_kb = kb + 1 == sched.k_blocks;
+          // accumulator-major order: slot 0's MMAs of a K-block go first, so that with kSub == 2 its epilogue starts
+          // (last K-block) and its slot may be refilled (first K-block) half a K-block before slot 1's
 #pragma unroll
-          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-            const uint64_t db = make_smem_desc(b_addr + k * b_kstep, 1024, b_lbo);
+          for (int sub = 0; sub < kSub; ++sub) {
+            if (kb == 0) {  // the epilogue of the tile that used this slot last must have drained it
+              mbar_wait(&tmem_empty[slot0 + sub], ap ^ 1);
+              tc_fence_after();
+            }
 #pragma unroll
-            for (int sub = 0; sub < kSub; ++sub) {
+            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
               const uint64_t da = make_smem_desc(a_addr + sub * a_sub + k * a_kstep, 1024, a_lbo);
+              const uint64_t db = make_smem_desc(b_addr + k * b_kstep, 1024, b_lbo);
               umma_bf16<kCta>(tmem_base + (slot0 + sub) * BLOCK_N, da, db, idesc, (kb | k) != 0);
             }
+            if (last_kb) umma_commit<kCta>(&tmem_full[slot0 + sub]);  // this accumulator is complete
           }
           umma_commit<kCta>(&empty_bar[stage]);  // frees the smem slot (both CTAs) when these MMAs retire
-          if (kb + 1 == sched.k_blocks) {
-            umma_commit<kCta>(&tmem_full[slot0]);
-            if (kSub == 2) umma_commit<kCta>(&tmem_full[1]);
-          }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -289,10 +290,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       c.tmem_acc = tmem_base + slot * BLOCK_N + ((quad * 32u) << 16);
       mbar_wait(&tmem_full[slot], ap);
       tc_fence_after();
-      Epi::run(ep, c, smem_epi);  // returns with all of its TMEM loads complete
-      tc_fence_before();
-      if (leader) mbar_arrive(&tmem_empty[slot]);
-      else mbar_arrive_cluster(&tmem_empty[slot], 0);
+      // the epilogue calls `release` as soon as its last TMEM load has completed, before it finishes the arithmetic
+      // and the stores of that last column group: the MMA warp can refill the slot that much earlier
+      auto release = [&]() {
+        tc_fence_before();
+        if (leader) mbar_arrive(&tmem_empty[slot]);
+        else mbar_arrive_cluster(&tmem_empty[slot], 0);
+      };
+      Epi::run(ep, c, smem_epi, release);
     }
   }
 
@@ -315,7 +320,8 @@ struct EpiF32 {
     uint32_t accumulate;
   };
   static constexpr int kSmemBytes = 0;
-  __device__ static void run(const Params& p, const EpiCtx& c, uint8_t*) {
+  template <class Release>
+  __device__ static void run(const Params& p, const EpiCtx& c, uint8_t*, Release&& release) {
     const uint32_t row = c.row, col0 = c.col0;
     float* out = p.c + static_cast<int64_t>(row) * p.ldc + col0;
 #pragma unroll 1
@@ -323,6 +329,7 @@ struct EpiF32 {
       uint32_t v[32];
       tmem_ld_32x32(c.tmem_acc + g * 32, v);
       tmem_ld_wait();
+      if (g == BLOCK_N / 32 - 1) release();
       if (row < p.m) {
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
@@ -356,7 +363,8 @@ struct EpiBF16 {
     int64_t ld_gather;
   };
   static constexpr int kSmemBytes = 0;
-  __device__ static void run(const Params& p, const EpiCtx& c, uint8_t*) {
+  template <class Release>
+  __device__ static void run(const Params& p, const EpiCtx& c, uint8_t*, Release&& release) {
     const uint32_t row = c.row, col0 = c.col0;
     const bool row_ok = row < p.m;
     __nv_bfloat16* out = p.c + static_cast<int64_t>(row) * p.ldc + col0;
@@ -368,6 +376,7 @@ struct EpiBF16 {
       uint32_t v[32];
       tmem_ld_32x32(c.tmem_acc + g * 32, v);
       tmem_ld_wait();
+      if (g == BLOCK_N / 32 - 1) release();
       if (row_ok) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {

@@ -66,13 +66,16 @@ struct EpiSoftmax {
   };
   static constexpr int kSmemBytes = 0;
 
-  __device__ static void run(const Params& p, const EpiCtx& c, uint8_t*) {
+  template <class Release>
+  __device__ static void run(const Params& p, const EpiCtx& c, uint8_t*, Release&& release) {
     const uint32_t row = c.row, col0 = c.col0;
     const bool row_ok = row < p.rows;
     const uint32_t ncols = min(static_cast<uint32_t>(BLOCK_N), p.vocab - col0);
     const uint32_t ngroups = (ncols + 31) >> 5;  // column groups of 32 that hold at least one real vocabulary entry
     const float c1 = p.scale * kLog2e;
-    const float off = (row_ok ? p.ref[row] : 0.f) * c1;
+    // rows past the last token get an infinite offset: every exponential is then exactly 0 (zeros in the stash) with no
+    // per-element select
+    const float off = row_ok ? p.ref[row] * c1 : INFINITY;
     const bool want_ez = p.part_ez != nullptr;
     // Every row of the tile is stored (zeros past the last token / past the vocabulary) so that the blocked stash
     // never exposes stale bytes to the backward GEMMs' zero-padded K tails.
@@ -88,14 +91,16 @@ struct EpiSoftmax {
       uint32_t v[32];
       tmem_ld_32x32(c.tmem_acc + g * 32, v);
       tmem_ld_wait();
+      if (g + 1 == ngroups) release();  // last TMEM read of this accumulator
       const uint32_t valid = ncols - g * 32;  // >= 1
       float e[32];
+      if (valid >= 32) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const float x = fminf(fmaf(__uint_as_float(v[i]), c1, -off), kClampLog2);
-        float ex = fast_exp2(x);
-        if (valid < 32 && static_cast<uint32_t>(i) >= valid) ex = 0.f;  // zero-filled columns past the vocabulary
-        e[i] = row_ok ? ex : 0.f;
+        for (int i = 0; i < 32; ++i) e[i] = fast_exp2(fminf(fmaf(__uint_as_float(v[i]), c1, -off), kClampLog2));
+      } else {  // only the last group of the last vocabulary tile: zero-filled columns past the vocabulary
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          e[i] = static_cast<uint32_t>(i) < valid ? fast_exp2(fminf(fmaf(__uint_as_float(v[i]), c1, -off), kClampLog2)) : 0.f;
       }
 #pragma unroll
       for (int i = 0; i < 32; i += 2) {
