@@ -146,7 +146,16 @@ def step_plan(local, micro_seqs):
 # ------------------------------------------------------------------------------------------------------------------
 # one step, device-resident inputs
 # ------------------------------------------------------------------------------------------------------------------
-def run_step_device(st, x, plan, dweight, world, temperature, want_entropy):
+def valid_counts(x, plan):
+    """Host-side count of unmasked tokens per micro-batch (the trainer knows the response lengths); None when dense."""
+    lens = x["lens"].cpu()
+    tlen = x["mask"].shape[1]
+    if bool((lens == tlen).all()):
+        return None
+    return {(sl.start, sl.stop): int(lens[sl].sum()) for mbs in plan for sl in mbs}
+
+
+def run_step_device(st, x, plan, dweight, world, temperature, want_entropy, counts=None):
     from spatialthinker_b200.sharding import allreduce_mean_
 
     # advantages: groups straddle ranks, so the per-sequence scores are all-gathered (B floats) and the group statistics
@@ -159,7 +168,8 @@ def run_step_device(st, x, plan, dweight, world, temperature, want_entropy):
         for sl in mbs:
             res = st.grpo_micro_batch_step(x["hidden"][sl], x["weight"], x["labels"][sl], x["old"][sl], adv[sl], x["ref"][sl],
                                            x["mask"][sl], temperature=temperature, grad_accum=ga, dweight_accum=dweight,
-                                           want_entropy=want_entropy, **CLIP, **KL)
+                                           want_entropy=want_entropy,
+                                           valid_rows=None if counts is None else counts[(sl.start, sl.stop)], **CLIP, **KL)
             metrics.append(res["metrics"])
         allreduce_mean_(dweight)
         norms.append(torch.linalg.vector_norm(dweight))
@@ -209,7 +219,7 @@ class HostFeed:
         self.free[slot].record(torch.cuda.current_stream(self.dev))
 
 
-def run_step_e2e(st, x, feed, plan, dweight, temperature, want_entropy, host_metrics):
+def run_step_e2e(st, x, feed, plan, dweight, temperature, want_entropy, host_metrics, counts=None):
     from spatialthinker_b200.sharding import allreduce_mean_
 
     flat = [(i, sl) for i, mbs in enumerate(plan) for sl in mbs]
@@ -222,7 +232,8 @@ def run_step_e2e(st, x, feed, plan, dweight, temperature, want_entropy, host_met
         mb = feed.get(slot, sl)
         res = st.grpo_micro_batch_step(mb["hidden"], x["weight"], mb["labels"], mb["old"], mb["adv"], mb["ref"], mb["mask"],
                                        temperature=temperature, grad_accum=float(len(plan[i])), dweight_accum=dweight,
-                                       want_entropy=want_entropy, **CLIP, **KL)
+                                       want_entropy=want_entropy,
+                                       valid_rows=None if counts is None else counts[(sl.start, sl.stop)], **CLIP, **KL)
         feed.release(slot)
         metrics.append(res["metrics"])
         if j + 1 == len(flat) or flat[j + 1][0] != i:
@@ -360,7 +371,8 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    dev_step = lambda: run_step_device(st, x, plan, dweight, world, 1.0, want_entropy)  # noqa: E731
+    counts = valid_counts(x, plan)
+    dev_step = lambda: run_step_device(st, x, plan, dweight, world, 1.0, want_entropy, counts)  # noqa: E731
     for _ in range(args.warmup):
         dev_step()
     sampler = ClockSampler(local_rank)
@@ -387,7 +399,7 @@ def main():
         feed = HostFeed(x, adv, plan, dev)
         n_rows = sum(len(m) for m in plan) + len(plan)
         host_metrics = torch.empty(n_rows, _lib.NUM_METRICS, dtype=torch.float32).pin_memory()
-        e2e_step = lambda: run_step_e2e(st, x, feed, plan, dweight, 1.0, want_entropy, host_metrics)  # noqa: E731
+        e2e_step = lambda: run_step_e2e(st, x, feed, plan, dweight, 1.0, want_entropy, host_metrics, counts)  # noqa: E731
         for _ in range(min(args.warmup, 1)):
             e2e_step()
         ms_e2e = timed(e2e_step, args.steps) / args.steps
@@ -406,7 +418,7 @@ def main():
             kernels.append({"name": name, "launches": int(ph_cnt[i]), "avg_ms": ph_ms[i] / ph_cnt[i], "total_ms": ph_ms[i]})
     gemms = [k for k in kernels if k["name"].endswith("_gemm")]
     dom = max(gemms, key=lambda k: k["total_ms"])
-    rows_per_launch = tokens_local * args.steps / dom["launches"]  # every GEMM launch covers one chunk of rows
+    rows_per_launch = tokens_local * args.steps / dom["launches"]  # every GEMM launch covers one chunk of (valid) rows
     achieved = 2.0 * hdim * vocab * rows_per_launch / (dom["avg_ms"] * 1e-3) / 1e12
     peak = peaks["sustained"]  # kernels are timed inside a seconds-long step under the power cap
     traffic = None

@@ -5,7 +5,7 @@ Host side: Python/PyTorch mirrors of the reference's call surface
 Device side: hand-written CUDA behind a C ABI (``include/grpo_b200.h`` -> ``libgrpo_b200.so``).
 There is no CPU fallback: every function raises if its CUDA library or a CUDA tensor is missing.
 """
-from . import core_algos, dp_actor, fused, sharding, torch_functional  # noqa: F401
+from . import core_algos, dp_actor, fused, hf_hook, sharding, torch_functional  # noqa: F401
 from ._lib import GrpoLibraryError, load as load_library  # noqa: F401
 from .core_algos import compute_grpo_outcome_advantage, compute_kl, compute_policy_loss, kl_penalty  # noqa: F401
 from .dp_actor import ActorConfig, DataParallelPPOActor  # noqa: F401

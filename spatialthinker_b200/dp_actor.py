@@ -73,6 +73,7 @@ class DataParallelPPOActor:
         actor_optimizer: Optional[torch.optim.Optimizer] = None,
         hidden_fn: Optional[Callable[[Dict[str, Any]], torch.Tensor]] = None,
         process_group: Optional["dist.ProcessGroup"] = None,
+        compact_padding: bool = True,
     ):
         self.config = config
         self.rank = int(os.getenv("RANK", "0"))
@@ -80,6 +81,9 @@ class DataParallelPPOActor:
         self.actor_optimizer = actor_optimizer
         self.hidden_fn = hidden_fn
         self.process_group = process_group
+        # drop padded token rows before the GEMMs (costs ONE device->host read of the per-micro-batch token counts per
+        # update_policy call; the reference computes log-probs for padding and multiplies them by 0)
+        self.compact_padding = compact_padding
         self.dweight: Optional[torch.Tensor] = None  # fp32 [V, H] accumulator ("main grad") across micro-batches
         self.last_dhidden: List[torch.Tensor] = []   # per micro-batch dHidden of the last update (when no hidden_fn)
 
@@ -155,11 +159,19 @@ class DataParallelPPOActor:
         pending: List[torch.Tensor] = []  # device metric vectors, one per micro-batch
         norms: List[torch.Tensor] = []
         self.last_dhidden = []
+        micro_lists = [mini_batch.split(cfg.micro_batch_size_per_device_for_update) for mini_batch in mini_batches]
+        counts = None
+        if self.compact_padding:
+            sums = [(self._response_mask({**mb.batch}) != 0).sum() for mbs in micro_lists for mb in mbs]
+            counts = torch.stack(sums).cpu().tolist() if sums else []
         for _ in range(cfg.ppo_epochs):
-            for mini_batch in mini_batches:
+            flat_i = 0
+            for micro_batches in micro_lists:
                 grad_accum = cfg.global_batch_size_per_device // cfg.micro_batch_size_per_device_for_update
-                for mb in mini_batch.split(cfg.micro_batch_size_per_device_for_update):
+                for mb in micro_batches:
                     micro = {**mb.batch, **mb.non_tensor_batch}
+                    valid_rows = counts[flat_i] if counts is not None else None
+                    flat_i += 1
                     hidden = self._hidden(micro, train=True)
                     step = grpo_micro_batch_step(
                         hidden.detach(), self.weight.detach(), micro["responses"], micro["old_log_probs"],
@@ -167,7 +179,7 @@ class DataParallelPPOActor:
                         temperature=temperature, clip_ratio_low=cfg.clip_ratio_low, clip_ratio_high=cfg.clip_ratio_high,
                         clip_ratio_dual=cfg.clip_ratio_dual, kl_penalty=cfg.kl_penalty if use_ref else None,
                         kl_coef=cfg.kl_coef, grad_accum=float(grad_accum), entropy_coeff=cfg.entropy_coeff,
-                        dweight_accum=self.dweight,
+                        dweight_accum=self.dweight, valid_rows=valid_rows,
                     )
                     if hidden.requires_grad:
                         hidden.backward(step["dhidden"])  # continue into the transformer body

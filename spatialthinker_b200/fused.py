@@ -132,6 +132,7 @@ def grpo_micro_batch_step(
     want_entropy: bool = False,
     dweight_accum: Optional[torch.Tensor] = None,
     need_grads: bool = True,
+    valid_rows: Optional[int] = None,
 ) -> Dict[str, torch.Tensor]:
     """Forward + backward of one micro-batch (dp_actor.py:247-278) entirely on the device, no host sync.
 
@@ -139,7 +140,20 @@ def grpo_micro_batch_step(
     by the ``_lib.MET_*`` slots), ``dhidden`` (bf16, gradient of ``loss = total / grad_accum``) and ``dweight`` - the
     fp32 ``[V, H]`` buffer the weight gradient was ACCUMULATED into (``dweight_accum`` if given, else a fresh zero
     buffer).
+
+    ``valid_rows`` (optional, a HOST integer = number of non-zero mask entries, e.g. the sum of the response lengths the
+    trainer already knows): padded positions are then dropped before the GEMMs - the reference computes and discards
+    them (dp_actor.py:136-139) - and the outputs are scattered back (``log_probs`` / ``entropy`` are 0 and ``dhidden``
+    rows are 0 at padded positions). Without the hint nothing is compacted, because finding the count would cost a
+    device->host sync.
     """
+    if valid_rows is not None and 0 < valid_rows < response_mask.numel():
+        return _compacted_step(hidden, weight, labels, old_log_probs, advantages, ref_log_probs, response_mask,
+                               int(valid_rows), dict(temperature=temperature, clip_ratio_low=clip_ratio_low,
+                                                     clip_ratio_high=clip_ratio_high, clip_ratio_dual=clip_ratio_dual,
+                                                     kl_penalty=kl_penalty, kl_coef=kl_coef, grad_accum=grad_accum,
+                                                     entropy_coeff=entropy_coeff, want_entropy=want_entropy,
+                                                     dweight_accum=dweight_accum, need_grads=need_grads))
     dev, h2, w2, lab = _check_head(hidden, weight, labels)
     lib = _lib.load()
     rows, hdim = h2.shape
@@ -188,6 +202,33 @@ def grpo_micro_batch_step(
         "dweight": dw,
         "used_kl": use_kl,
     }
+
+
+def _compacted_step(hidden, weight, labels, old_log_probs, advantages, ref_log_probs, response_mask, valid_rows, kw):
+    """Gather the ``valid_rows`` unmasked token rows, run the fused step on them, scatter the results back."""
+    lead = hidden.shape[:-1]
+    hdim = hidden.shape[-1]
+    flat_mask = response_mask.reshape(-1)
+    # stable sort puts the unmasked rows first, in their original order; the count is known on the host: no sync
+    order = torch.argsort((flat_mask != 0).to(torch.int8), descending=True, stable=True)
+    idx = order[:valid_rows]
+    take = lambda t: None if t is None else t.reshape(-1).index_select(0, idx)  # noqa: E731
+    res = grpo_micro_batch_step(
+        hidden.reshape(-1, hdim).index_select(0, idx), weight, take(labels), take(old_log_probs), take(advantages),
+        take(ref_log_probs), take(flat_mask), **kw)
+    dev = hidden.device
+    logp = torch.zeros(flat_mask.numel(), dtype=torch.float32, device=dev)
+    logp.index_copy_(0, idx, res["log_probs"])
+    res["log_probs"] = logp.view(*lead)
+    if res["entropy"] is not None:
+        ent = torch.zeros(flat_mask.numel(), dtype=torch.float32, device=dev)
+        ent.index_copy_(0, idx, res["entropy"])
+        res["entropy"] = ent.view(*lead)
+    if res["dhidden"] is not None:
+        dh = torch.zeros(flat_mask.numel(), hdim, dtype=torch.bfloat16, device=dev)
+        dh.index_copy_(0, idx, res["dhidden"])
+        res["dhidden"] = dh.view(hidden.shape)
+    return res
 
 
 def metrics_to_dict(metrics: torch.Tensor, used_kl: bool, kl_coef: float) -> Dict[str, float]:

@@ -417,6 +417,37 @@ def test_improbable_labels_and_garbage_padding(st, dev):
     assert bool(torch.isfinite(met["log_probs"]).all())
 
 
+def test_padding_compaction_is_equivalent(st, dev):
+    """valid_rows (host-known count of unmasked tokens) drops padded rows before the GEMMs; nothing else may change."""
+    x = _loss_inputs(8, 96, 128, 4096, 4, 0.1, seed=131, ragged=True)
+    d = {k: x[k].to(dev) for k in ("hidden", "weight", "labels", "old", "adv", "ref", "mask")}
+    n_valid = int(x["mask"].sum())
+    assert 0 < n_valid < x["mask"].numel()
+    kw = dict(temperature=0.9, kl_penalty="low_var_kl", kl_coef=0.02, grad_accum=2.0, want_entropy=True)
+    full = st.grpo_micro_batch_step(d["hidden"], d["weight"], d["labels"], d["old"], d["adv"], d["ref"], d["mask"], **kw)
+    comp = st.grpo_micro_batch_step(d["hidden"], d["weight"], d["labels"], d["old"], d["adv"], d["ref"], d["mask"],
+                                    valid_rows=n_valid, **kw)
+    valid = x["mask"].bool().to(dev)
+    np.testing.assert_allclose(comp["metrics"].cpu().numpy(), full["metrics"].cpu().numpy(), rtol=2e-5, atol=1e-7)
+    assert float((comp["log_probs"] - full["log_probs"])[valid].abs().max()) < 1e-5
+    assert float(comp["log_probs"][~valid].abs().max()) == 0.0
+    assert rel(comp["dhidden"], full["dhidden"]) < 2e-3 and float(comp["dhidden"][~valid].abs().max()) == 0.0
+    assert rel(comp["dweight"], full["dweight"]) < 2e-3
+    # and against the oracle
+    want = O.fused_loss_reference(x["hidden"], x["weight"], x["labels"], x["old"], x["adv"], x["mask"], x["ref"],
+                                  temperature=0.9, kl_penalty="low_var_kl", kl_coef=0.02, grad_accum=2.0)
+    assert rel(comp["dhidden"], want["dhidden"]) < TOL_REL and rel(comp["dweight"], want["dweight"]) < TOL_REL
+    # the actor loop uses it by default: same metrics with and without
+    cfg = st.ActorConfig(global_batch_size_per_device=8, micro_batch_size_per_device_for_update=4, use_kl_loss=True,
+                         kl_penalty="low_var_kl", kl_coef=0.02)
+    batch = {"hidden_states": d["hidden"], "responses": d["labels"], "response_mask": d["mask"], "old_log_probs": d["old"],
+             "advantages": d["adv"], "ref_log_probs": d["ref"]}
+    m1 = st.DataParallelPPOActor(cfg, d["weight"], compact_padding=True).update_policy(st.TensorBatch(batch, meta_info={"temperature": 0.9}))
+    m0 = st.DataParallelPPOActor(cfg, d["weight"], compact_padding=False).update_policy(st.TensorBatch(batch, meta_info={"temperature": 0.9}))
+    for key in ("actor/pg_loss", "actor/ppo_kl", "actor/entropy_loss", "actor/grad_norm"):
+        np.testing.assert_allclose(m1[key], m0[key], rtol=2e-3, atol=1e-6)
+
+
 def test_config_c1_full_head(st, dev):
     """BASELINE.json configs[0]: Qwen2.5-VL-3B head (H 2048, V 151936), 8 rollouts x 512 response tokens, against the
     fp32 CPU oracle - log-probs, entropy, advantages, loss, dHidden, dW."""
