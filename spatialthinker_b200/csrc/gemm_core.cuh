@@ -48,6 +48,7 @@ struct TileSched {
   uint32_t* sync_ctr;    // zeroed by the host before the launch
   // L2 eviction priority of the two operand streams (kEvictNormal / kEvictFirst / kEvictLast)
   uint64_t hint_a, hint_b;
+  uint32_t wait_hint_ns;  // suspend-time hint of the epilogue warps' mbarrier waits (0: poll)
 };
 
 // Progress window `round` (1-based) starts: announce it, then make sure every one of the `groups` producers has at least
@@ -288,7 +289,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       c.row = m_blk * Cfg::kTileRows + rank * Cfg::kRowsPerCta + grp * kBlockM + quad * 32 + lane;
       c.col0 = c.n_blk * BLOCK_N;
       c.tmem_acc = tmem_base + slot * BLOCK_N + ((quad * 32u) << 16);
-      mbar_wait(&tmem_full[slot], ap);
+      mbar_wait(&tmem_full[slot], ap, sched.wait_hint_ns);
       tc_fence_after();
       // the epilogue calls `release` as soon as its last TMEM load has completed, before it finishes the arithmetic
       // and the stores of that last column group: the MMA warp can refill the slot that much earlier

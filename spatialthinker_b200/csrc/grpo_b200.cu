@@ -172,6 +172,7 @@ struct Knobs {
   int l2_hints = 0;
   int dh_m_fast = 0;   // tile order of the dHidden GEMM (experiment)
   int chunk_rows = 0;  // rows per chunk of the pipeline (0: 37 row tiles, see default_chunk_rows)
+  int wait_hint_ns = 10000000;  // suspend hint of the epilogue warps' accumulator-ready wait (0: busy poll)
 };
 static Knobs g_knobs;
 static std::once_flag g_knobs_once;
@@ -190,6 +191,7 @@ static void init_knobs() {
     g_knobs.l2_hints = env_int("GRPO_L2_HINTS", g_knobs.l2_hints);
     g_knobs.dh_m_fast = env_int("GRPO_DH_M_FAST", g_knobs.dh_m_fast);
     g_knobs.chunk_rows = env_int("GRPO_CHUNK_ROWS", g_knobs.chunk_rows);
+    g_knobs.wait_hint_ns = env_int("GRPO_WAIT_HINT_NS", g_knobs.wait_hint_ns);
   });
 }
 
@@ -273,6 +275,7 @@ static int launch_gemm_any(const DevInfo& dev, const void* a, uint64_t a_rows, u
   if (sched.panel_m == 0 || sched.panel_m > sched.m_blocks) sched.panel_m = sched.m_blocks;
   if (sched.hint_a == 0) sched.hint_a = kEvictNormal;
   if (sched.hint_b == 0) sched.hint_b = kEvictNormal;
+  sched.wait_hint_ns = static_cast<uint32_t>(dev.wait_hint_ns);
   if (cta_group == 1) return launch_gemm<1, 1, kBlockN, kStages11, kAMode, kBMn, Epi1>(ta, tb, sched, ep1, dev.sms, stream);
   if (ksub == 1) return launch_gemm<2, 1, kBlockN, kStages21, kAMode, kBMn, Epi2>(ta, tb, sched, ep2, dev.sms, stream);
   return launch_gemm<2, 2, kBlockN, kStages22, kAMode, kBMn, Epi2>(ta, tb, sched, ep2, dev.sms, stream);
@@ -495,6 +498,7 @@ int grpo_set_option(const char* name, int value) {
   else if (!strcmp(name, "sync_dw")) g_knobs.sync_dw = value;
   else if (!strcmp(name, "l2_hints")) g_knobs.l2_hints = value;
   else if (!strcmp(name, "dh_m_fast")) g_knobs.dh_m_fast = value;
+  else if (!strcmp(name, "wait_hint_ns")) g_knobs.wait_hint_ns = value < 0 ? 0 : value;
   else if (!strcmp(name, "chunk_rows")) g_knobs.chunk_rows = value > 0 ? (value + 511) / 512 * 512 : 0;
   else return fail(GRPO_ERR_ARG, "unknown option '%s'", name);
   return 0;

@@ -57,23 +57,27 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
 }
-__device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity) {
+// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes (or the hint expires)
+// instead of spinning - the eight epilogue warps wait ~60k cycles per tile and would otherwise burn issue slots and
+// power polling (24 % of all warp samples in the first profile of the wide-tile kernel).
+constexpr uint32_t kWaitHintNs = 0x989680u;
+__device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity, uint32_t hint_ns = kWaitHintNs) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.b32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns) : "memory");
   return ok;
 }
 // Bounded wait: a protocol bug becomes a trap (launch failure) instead of a hung GPU.
 #ifndef GRPO_MBAR_TIMEOUT_CYCLES
 #define GRPO_MBAR_TIMEOUT_CYCLES 6000000000ll
 #endif
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t hint_ns = kWaitHintNs) {
+  if (mbar_try_wait(bar, parity, hint_ns)) return;
   const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
+  while (!mbar_try_wait(bar, parity, hint_ns)) {
     if (clock64() - t0 > GRPO_MBAR_TIMEOUT_CYCLES) {
       printf("grpo: mbarrier timeout block %d thread %d bar %u parity %u\n", (int)blockIdx.x, (int)threadIdx.x,
              smem_u32(bar), parity);
