@@ -29,6 +29,7 @@ _SIGNATURES = {
     "grpo_last_error": (c_char_p, []),
     "grpo_launch_count": (ctypes.c_longlong, []),
     "grpo_set_option": (c_int, [c_char_p, c_int]),
+    "grpo_debug_probe_offset": (c_size_t, [c_int64, c_int64, c_int64, c_int]),
     "grpo_profile_enable": (c_int, [c_int]),
     "grpo_profile_read": (c_int, [_P, _P, c_int]),
     "grpo_lmhead_fwd_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),

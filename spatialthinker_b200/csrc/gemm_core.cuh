@@ -49,6 +49,10 @@ struct TileSched {
   // L2 eviction priority of the two operand streams (kEvictNormal / kEvictFirst / kEvictLast)
   uint64_t hint_a, hint_b;
   uint32_t wait_hint_ns;  // suspend-time hint of the epilogue warps' mbarrier waits (0: poll)
+  // measurement aid: block 0 writes {clock64, globaltimer} at entry and exit (4 x u64) so that the SM clock a kernel
+  // actually ran at inside a long pipeline can be read back (nullptr: off)
+  unsigned long long* probe;
+  uint32_t acc_lead;      // wide tile: K-blocks accumulator 0 runs ahead of accumulator 1 at the tile ends (0..kStages-1)
 };
 
 // Progress window `round` (1-based) starts: announce it, then make sure every one of the `groups` producers has at least
@@ -95,7 +99,10 @@ struct EpiCtx {
   uint32_t col0;      // first global column of the accumulator
   uint32_t warp, lane;
   uint32_t tmem_acc;  // TMEM address of this warp's lanes, column 0 of the accumulator
+  uint32_t epi_warp;  // index of this warp among the CTA's epilogue warps (its 4 KB staging buffer in smem_epi)
+  uint32_t row0;      // first global output row of this warp (row - lane)
 };
+constexpr int kEpiStageBytes = 4096;  // per-epilogue-warp staging buffer for shared -> global bulk stores
 
 // kSub = number of 128-row accumulators a CTA computes per tile (its share of the tile is 128 * kSub rows):
 //   kSub == 1: 128 x BLOCK_N per CTA; the two TMEM accumulator slots double-buffer consecutive tiles, so the epilogue
@@ -128,7 +135,7 @@ struct GemmCfg {
 template <int kCta, int kSub, int BLOCK_N, int kStages, int kAMode, bool kBMn, class Epi>
 __global__ void __launch_bounds__(128 + 128 * kSub, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-            const TileSched sched, const typename Epi::Params ep) {
+            const TileSched sched, const __grid_constant__ typename Epi::Params ep) {
   using Cfg = GemmCfg<kCta, kSub, BLOCK_N, kStages>;
   constexpr bool kAMn = (kAMode & 1) != 0;
   extern __shared__ uint8_t smem_raw[];
@@ -151,6 +158,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+  }
+  // warp 3 has no other role. Layout: [0..3] block 0 {clock64, ns} at entry / exit; [8 + 2g], [9 + 2g] entry / exit ns of
+  // CTA group g (how far apart the persistent groups start and finish)
+  const bool probing = sched.probe != nullptr && threadIdx.x == 96 && rank == 0;
+  if (probing) {
+    unsigned long long ns;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+    if (blockIdx.x == 0) {
+      sched.probe[0] = static_cast<unsigned long long>(clock64());
+      sched.probe[1] = ns;
+    }
+    if (blockIdx.x / kCta < 120) sched.probe[8 + 2 * (blockIdx.x / kCta)] = ns;
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) {
@@ -231,35 +250,60 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       constexpr uint32_t a_lbo = kAMn ? kBlockK * 128 : 0, b_lbo = kBMn ? kBlockK * 128 : 0;
       constexpr uint32_t a_kstep = kAMn ? kUmmaK * 128 : kUmmaK * 2, b_kstep = kBMn ? kUmmaK * 128 : kUmmaK * 2;
       constexpr uint32_t a_sub = kBlockM * 128;  // 128 rows further on: 16 KB in either majorness (two 8 KB MN atoms)
-      uint32_t stage = 0, phase = 0, it = 0;
-      for (uint32_t t = first_tile; t < num_tiles; t += tile_step, ++it) {
+      uint32_t it = 0, base = 0;  // base: K-blocks issued before this tile (ring position of its K-block 0)
+      const uint32_t kblocks = sched.k_blocks;
+      for (uint32_t t = first_tile; t < num_tiles; t += tile_step, ++it, base += kblocks) {
         // accumulator slots: kSub == 1 alternates them tile by tile, kSub == 2 uses both for every tile
         const uint32_t slot0 = (kSub == 1) ? (it & 1) : 0u;
         const uint32_t ap = (kSub == 1) ? ((it >> 1) & 1) : (it & 1);
-        for (uint32_t kb = 0; kb < sched.k_blocks; ++kb) {
+        // the MMAs of accumulator `sub` for K-block `kb` of this tile
+        auto issue = [&](uint32_t sub, uint32_t kb) {
+          const uint32_t cnt = base + kb, stage = cnt % kStages, phase = (cnt / kStages) & 1;
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
+          if (kb == 0) {  // the epilogue of the tile that used this slot last must have drained it
+            mbar_wait(&tmem_empty[slot0 + sub], ap ^ 1);
+            tc_fence_after();
+          }
           const uint32_t a_addr = smem_u32(smem_a + stage * Cfg::kABytes);
           const uint32_t b_addr = smem_u32(smem_b + stage * Cfg::kBBytes);
-          const bool last_kb = kb + 1 == sched.k_blocks;
-          // accumulator-major order: slot 0's MMAs of a K-block go first, so that with kSub == 2 its epilogue starts
-          // (last K-block) and its slot may be refilled (first K-block) half a K-block before slot 1's
 #pragma unroll
-          for (int sub = 0; sub < kSub; ++sub) {
-            if (kb == 0) {  // the epilogue of the tile that used this slot last must have drained it
-              mbar_wait(&tmem_empty[slot0 + sub], ap ^ 1);
-              tc_fence_after();
-            }
-#pragma unroll
-            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-              const uint64_t da = make_smem_desc(a_addr + sub * a_sub + k * a_kstep, 1024, a_lbo);
-              const uint64_t db = make_smem_desc(b_addr + k * b_kstep, 1024, b_lbo);
-              umma_bf16<kCta>(tmem_base + (slot0 + sub) * BLOCK_N, da, db, idesc, (kb | k) != 0);
-            }
-            if (last_kb) umma_commit<kCta>(&tmem_full[slot0 + sub]);  // this accumulator is complete
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            const uint64_t da = make_smem_desc(a_addr + sub * a_sub + k * a_kstep, 1024, a_lbo);
+            const uint64_t db = make_smem_desc(b_addr + k * b_kstep, 1024, b_lbo);
+            umma_bf16<kCta>(tmem_base + (slot0 + sub) * BLOCK_N, da, db, idesc, (kb | k) != 0);
           }
-          umma_commit<kCta>(&empty_bar[stage]);  // frees the smem slot (both CTAs) when these MMAs retire
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (kb + 1 == kblocks) umma_commit<kCta>(&tmem_full[slot0 + sub]);  // this accumulator is complete
+        };
+        // frees the smem slot of K-block `kb` (both CTAs) when the MMAs issued so far retire
+        auto free_stage = [&](uint32_t kb) { umma_commit<kCta>(&empty_bar[(base + kb) % kStages]); };
+        if constexpr (kSub == 1) {
+          for (uint32_t kb = 0; kb < kblocks; ++kb) {
+            issue(0, kb);
+            free_stage(kb);
+          }
+        } else {
+          // Accumulator 0 runs `lead` K-blocks ahead of accumulator 1 at both ends of the tile (in between they share
+          // every B stage back to back): its epilogue starts - and its slot is free again for the next tile - that much
+          // earlier, so the two drains overlap the other accumulator's MMAs instead of both idling the tensor pipe.
+          // The ring simply holds `lead` stages a little longer at the two ends.
+          uint32_t lead = sched.acc_lead < kStages - 1 ? sched.acc_lead : kStages - 1;
+          if (kblocks < 2 * lead) lead = 0;
+          for (uint32_t kb = 0; kb < lead; ++kb) issue(0, kb);
+          for (uint32_t kb = 0; kb < lead; ++kb) {
+            issue(1, kb);
+            free_stage(kb);
+          }
+          for (uint32_t kb = lead; kb + lead < kblocks; ++kb) {
+            issue(0, kb);
+            issue(1, kb);
+            free_stage(kb);
+          }
+          for (uint32_t kb = kblocks - lead; kb < kblocks; ++kb) issue(0, kb);
+          for (uint32_t kb = kblocks - lead; kb < kblocks; ++kb) {
+            issue(1, kb);
+            free_stage(kb);
+          }
         }
       }
       // the peer's last remote arrivals must land before this CTA's barriers go away
@@ -286,7 +330,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       decode_tile(sched, t, m_blk, c.n_blk);
       c.warp = quad;
       c.lane = lane;
-      c.row = m_blk * Cfg::kTileRows + rank * Cfg::kRowsPerCta + grp * kBlockM + quad * 32 + lane;
+      c.epi_warp = ew;
+      c.row0 = m_blk * Cfg::kTileRows + rank * Cfg::kRowsPerCta + grp * kBlockM + quad * 32;
+      c.row = c.row0 + lane;
       c.col0 = c.n_blk * BLOCK_N;
       c.tmem_acc = tmem_base + slot * BLOCK_N + ((quad * 32u) << 16);
       mbar_wait(&tmem_full[slot], ap, sched.wait_hint_ns);
@@ -300,30 +346,86 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       };
       Epi::run(ep, c, smem_epi, release);
     }
+    Epi::finish(ep, lane);  // outstanding bulk stores of this warp
   }
 
   __syncwarp();  // re-converge the single-lane roles before the aligned barriers below
   tc_fence_before();
   if (kCta == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 2) tmem_dealloc<kCta>(tmem_base, Cfg::kTmemCols);
+  if (probing) {
+    unsigned long long ns;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+    if (blockIdx.x == 0) {
+      sched.probe[2] = static_cast<unsigned long long>(clock64());
+      sched.probe[3] = ns;
+    }
+    if (blockIdx.x / kCta < 120) sched.probe[9 + 2 * (blockIdx.x / kCta)] = ns;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
 // Generic epilogues
 // ------------------------------------------------------------------------------------------
-// fp32 result, plain store or accumulate (red.global.add) into C[M][ldc].
+// fp32 result, plain store or accumulate into C[M][ldc].
+//   use_tma == 0: every thread stores / red.global.add's its own row, 16 bytes at a time (32 rows per warp instruction).
+//   use_tma != 0: each warp stages 32 rows x 32 columns (4 KB, 128-byte swizzle, conflict-free st.shared) and one lane
+//                 issues a bulk tensor store / reduce-add: the accumulation happens at L2 in whole 128-byte rows instead
+//                 of 16-byte pieces in 32 different lines per instruction, and the SM's LSU sees none of it.
 template <int kCta, int BLOCK_N>
 struct EpiF32 {
-  struct Params {
+  struct alignas(64) Params {
+    CUtensorMap c_map;  // fp32 [m][n] (row pitch ldc), box 32 x 32, SWIZZLE_128B; valid iff use_tma
     float* c;
     int64_t ldc;
     uint32_t m, n;
     uint32_t accumulate;
+    uint32_t use_tma;
+    uint64_t policy;  // L2 eviction priority of the bulk reduce-add (kEvictNormal / kEvictFirst)
   };
-  static constexpr int kSmemBytes = 0;
+  static constexpr int kSmemBytes = 8 * kEpiStageBytes;
+  __device__ static void finish(const Params& p, uint32_t lane) {
+    if (p.use_tma && lane == 0) bulk_wait_all();
+  }
   template <class Release>
-  __device__ static void run(const Params& p, const EpiCtx& c, uint8_t*, Release&& release) {
+  __device__ static void run(const Params& p, const EpiCtx& c, uint8_t* smem_epi, Release&& release) {
     const uint32_t row = c.row, col0 = c.col0;
+    if (p.use_tma) {
+      uint8_t* buf = smem_epi + c.epi_warp * kEpiStageBytes;
+      uint8_t* myrow = buf + c.lane * 128;
+      const uint32_t sw = c.lane & 7;
+      const bool rows_live = c.row0 < p.m;  // warp-uniform; rows past m inside a live box are clipped by the TMA unit
+      uint32_t va[32], vb[32];
+      auto emit = [&](const uint32_t (&v)[32], int g) {
+        const uint32_t col = col0 + g * 32;
+        if (!rows_live || col >= p.n) return;
+        if (c.lane == 0) bulk_wait_read_all();  // the previous copy out of this buffer has been read
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          st_shared_v4(myrow + ((q ^ sw) << 4), v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (c.lane == 0) {
+          if (p.accumulate) tma_reduce_add_2d(&p.c_map, buf, static_cast<int32_t>(col), static_cast<int32_t>(c.row0), p.policy);
+          else tma_store_2d(&p.c_map, buf, static_cast<int32_t>(col), static_cast<int32_t>(c.row0));
+          bulk_commit();
+        }
+      };
+      static_assert((BLOCK_N / 32) % 2 == 0, "column groups are drained in pairs");
+      tmem_ld_32x32(c.tmem_acc, va);
+#pragma unroll 1
+      for (int g = 0; g < BLOCK_N / 32; g += 2) {
+        tmem_ld_wait();
+        tmem_ld_32x32(c.tmem_acc + (g + 1) * 32, vb);
+        emit(va, g);
+        tmem_ld_wait();
+        if (g + 2 < BLOCK_N / 32) tmem_ld_32x32(c.tmem_acc + (g + 2) * 32, va);
+        else release();
+        emit(vb, g + 1);
+      }
+      return;
+    }
     float* out = p.c + static_cast<int64_t>(row) * p.ldc + col0;
 #pragma unroll 1
     for (int g = 0; g < BLOCK_N / 32; ++g) {
@@ -364,6 +466,7 @@ struct EpiBF16 {
     int64_t ld_gather;
   };
   static constexpr int kSmemBytes = 0;
+  __device__ static void finish(const Params&, uint32_t) {}
   template <class Release>
   __device__ static void run(const Params& p, const EpiCtx& c, uint8_t*, Release&& release) {
     const uint32_t row = c.row, col0 = c.col0;

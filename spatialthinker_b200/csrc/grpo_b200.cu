@@ -125,18 +125,36 @@ static int make_tmap_bf16(CUtensorMap* map, const void* base, uint64_t inner, ui
 
 // Blocked bf16 operand [blk3][blk2][64][64] (64 x 64 blocks of 8 KB, inner row = 128 B); box = (64, 64, box2, box3).
 static int make_tmap_blocked(CUtensorMap* map, const void* base, uint64_t n_blk2, uint64_t n_blk3, uint64_t blk3_pitch,
-                             uint32_t box2, uint32_t box3) {
+                             uint32_t box2, uint32_t box3, uint32_t box_rows = 64) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail(GRPO_ERR_DRIVER, "cuTensorMapEncodeTiled entry point not available");
   if (reinterpret_cast<uintptr_t>(base) & 15u) return fail(GRPO_ERR_ARG, "TMA operand must be 16-byte aligned");
   const cuuint64_t dims[4] = {64, 64, n_blk2, n_blk3};
   const cuuint64_t strides[3] = {128, 8192, blk3_pitch * 8192};
-  const cuuint32_t box[4] = {64, 64, box2, box3};
+  const cuuint32_t box[4] = {64, box_rows, box2, box3};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(GRPO_ERR_DRIVER, "cuTensorMapEncodeTiled (blocked) failed with CUresult %d", (int)r);
+  return 0;
+}
+
+// fp32 matrix [rows][cols] (row pitch `pitch_elems`), box 32 x 32 (128-byte rows, 128-byte swizzle): the epilogue's
+// bulk store / reduce-add target.
+static int make_tmap_f32_out(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, uint64_t pitch_elems) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(GRPO_ERR_DRIVER, "cuTensorMapEncodeTiled entry point not available");
+  if ((reinterpret_cast<uintptr_t>(base) & 15u) || (pitch_elems * 4) % 16 != 0)
+    return fail(GRPO_ERR_ARG, "fp32 output must be 16-byte aligned with a 16-byte multiple row pitch");
+  const cuuint64_t dims[2] = {cols, rows};
+  const cuuint64_t strides[1] = {pitch_elems * 4};
+  const cuuint32_t box[2] = {32, 32};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(GRPO_ERR_DRIVER, "cuTensorMapEncodeTiled (fp32 out) failed with CUresult %d", (int)r);
   return 0;
 }
 
@@ -173,6 +191,13 @@ struct Knobs {
   int dh_m_fast = 0;   // tile order of the dHidden GEMM (experiment)
   int chunk_rows = 0;  // rows per chunk of the pipeline (0: 37 row tiles, see default_chunk_rows)
   int wait_hint_ns = 10000000;  // suspend hint of the epilogue warps' accumulator-ready wait (0: busy poll)
+  // softmax epilogue of the logits GEMM, bit 0: software-pipelined TMEM drain, bit 1: exp-stash through shared memory +
+  // bulk tensor stores (EpiSoftmax::Params::mode)
+  int epi_mode = 3;
+  int acc_lead = 2;    // wide tile: accumulator 0's lead over accumulator 1 at the tile ends, in K-blocks (TileSched::acc_lead)
+  int st_hint = 3;     // bit 0: stash bulk stores evict-first, bit 1: dW bulk reduce-adds evict-first (else normal)
+  int clk_probe = 0;   // 1: the GEMM kernels record clock64 / globaltimer at entry and exit (grpo_debug_probe_offset)
+  int dw_tma = 1;      // dW GEMM epilogue: 1 = bulk tensor reduce-add from shared memory, 0 = per-thread red.global.add
 };
 static Knobs g_knobs;
 static std::once_flag g_knobs_once;
@@ -192,6 +217,9 @@ static void init_knobs() {
     g_knobs.dh_m_fast = env_int("GRPO_DH_M_FAST", g_knobs.dh_m_fast);
     g_knobs.chunk_rows = env_int("GRPO_CHUNK_ROWS", g_knobs.chunk_rows);
     g_knobs.wait_hint_ns = env_int("GRPO_WAIT_HINT_NS", g_knobs.wait_hint_ns);
+    g_knobs.epi_mode = env_int("GRPO_EPI_MODE", g_knobs.epi_mode) & 3;
+    g_knobs.dw_tma = env_int("GRPO_DW_TMA", g_knobs.dw_tma) != 0;
+    g_knobs.acc_lead = env_int("GRPO_ACC_LEAD", g_knobs.acc_lead);
   });
 }
 
@@ -276,6 +304,7 @@ static int launch_gemm_any(const DevInfo& dev, const void* a, uint64_t a_rows, u
   if (sched.hint_a == 0) sched.hint_a = kEvictNormal;
   if (sched.hint_b == 0) sched.hint_b = kEvictNormal;
   sched.wait_hint_ns = static_cast<uint32_t>(dev.wait_hint_ns);
+  sched.acc_lead = static_cast<uint32_t>(dev.acc_lead);
   if (cta_group == 1) return launch_gemm<1, 1, kBlockN, kStages11, kAMode, kBMn, Epi1>(ta, tb, sched, ep1, dev.sms, stream);
   if (ksub == 1) return launch_gemm<2, 1, kBlockN, kStages21, kAMode, kBMn, Epi2>(ta, tb, sched, ep2, dev.sms, stream);
   return launch_gemm<2, 2, kBlockN, kStages22, kAMode, kBMn, Epi2>(ta, tb, sched, ep2, dev.sms, stream);
@@ -295,7 +324,9 @@ struct Workspace {
   float *a_label = nullptr, *lse = nullptr, *inv_sum = nullptr, *dlogp = nullptr, *dent = nullptr, *ent = nullptr;
   float *row_scale = nullptr, *onehot = nullptr;
   double* acc = nullptr;
-  uint32_t* sync = nullptr;  // progress-barrier counters, one per GEMM of the chunk pipeline
+  uint32_t* sync = nullptr;  // progress-barrier counters, one per GEMM of the chunk pipeline (first 64 bytes)
+  unsigned long long* probe = nullptr;  // clock probes of the three GEMMs, 256 x u64 each (measurement aid)
+  size_t probe_offset = 0;
   size_t bytes = 0;
 };
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -333,7 +364,9 @@ static Workspace carve(void* base, int64_t rows, int64_t hdim, int64_t vocab, bo
   w.row_scale = reinterpret_cast<float*>(take(vec));
   w.onehot = reinterpret_cast<float*>(take(vec));
   w.acc = reinterpret_cast<double*>(take(ACC_N * sizeof(double)));
-  w.sync = reinterpret_cast<uint32_t*>(take(64));
+  w.probe_offset = off + 64;
+  w.sync = reinterpret_cast<uint32_t*>(take(64 + 3 * 2048));
+  w.probe = p ? reinterpret_cast<unsigned long long*>(p + w.probe_offset) : nullptr;
   w.bytes = off;
   return w;
 }
@@ -363,6 +396,13 @@ static int chunk_forward(const DevInfo& dev, const Workspace& w, const __nv_bflo
     GRPO_CUDA(cudaGetLastError());
   }
   EpiSoftmax<1, kBlockN>::Params p1;
+  memset(&p1, 0, sizeof(p1));
+  p1.mode = static_cast<uint32_t>(dev.epi_mode);
+  p1.policy = (dev.st_hint & 1) ? kEvictFirst : kEvictNormal;
+  if (!want_stash || !(p1.mode & 1)) p1.mode &= 1u;
+  if (p1.mode & 2)  // store view of the blocked stash: 32 rows x 64 columns (4 KB, contiguous in HBM) per bulk store
+    GRPO_TRY(make_tmap_blocked(&p1.stash_map, w.stash, static_cast<uint64_t>(w.stash_vb),
+                               static_cast<uint64_t>(w.rows_pad / 64), static_cast<uint64_t>(w.stash_vb), 1, 1, 32));
   p1.rows = static_cast<uint32_t>(n);
   p1.vocab = static_cast<uint32_t>(v);
   p1.rows_pad = static_cast<uint32_t>(w.rows_pad);
@@ -384,6 +424,7 @@ static int chunk_forward(const DevInfo& dev, const Workspace& w, const __nv_bflo
   }
   s.sync_period = static_cast<uint32_t>(dev.sync_fwd);
   s.sync_ctr = w.sync;
+  s.probe = dev.clk_probe ? w.probe : nullptr;
   if (dev.l2_hints & 1) {  // the hidden panel is re-read under every vocab tile; a W tile is dead after one panel pass
     s.hint_a = kEvictLast;
     s.hint_b = kEvictFirst;
@@ -437,17 +478,30 @@ static int chunk_backward(const DevInfo& dev, const Workspace& w, const __nv_bfl
     s.m_fast = static_cast<uint32_t>(dev.dh_m_fast);  // 0: all H column blocks of a few row blocks run together
     s.sync_period = static_cast<uint32_t>(dev.sync_dh);
     s.sync_ctr = w.sync + 1;
+    s.probe = dev.clk_probe ? w.probe + 256 : nullptr;
     GRPO_TRY((launch_gemm_any<A_BLOCKED_K, true, EpiBF16<1, kBlockN>, EpiBF16<2, kBlockN>>(
         dev, w.stash, n, w.stash_vb, weight, h, h, v, s, p1, p2, stream)));
   }
   {  // dW[v][h] += E^T[v][n] . hd[n][h]    A = stash read transposed (MN-major), B = (scaled) hidden read transposed
     PhaseScope ps(PH_DW_GEMM, stream);
-    EpiF32<1, kBlockN>::Params p1{dweight, h, uv, uh, 1u};
-    EpiF32<2, kBlockN>::Params p2{dweight, h, uv, uh, 1u};
+    EpiF32<1, kBlockN>::Params p1;
+    memset(&p1, 0, sizeof(p1));
+    p1.c = dweight;
+    p1.ldc = h;
+    p1.m = uv;
+    p1.n = uh;
+    p1.accumulate = 1u;
+    p1.use_tma = dev.dw_tma ? 1u : 0u;
+    p1.policy = (dev.st_hint & 2) ? kEvictFirst : kEvictNormal;
+    if (p1.use_tma) GRPO_TRY(make_tmap_f32_out(&p1.c_map, dweight, uh, uv, uh));
+    EpiF32<2, kBlockN>::Params p2;
+    static_assert(sizeof(p1) == sizeof(p2), "epilogue params layout");
+    memcpy(&p2, &p1, sizeof(p1));
     TileSched s{};
     s.m_fast = 0;  // the H column blocks of one vocab block run together: the stash panel is read from HBM once
     s.sync_period = static_cast<uint32_t>(dev.sync_dw);
     s.sync_ctr = w.sync + 2;
+    s.probe = dev.clk_probe ? w.probe + 512 : nullptr;
     if (dev.l2_hints & 2) {  // the (scaled) hidden chunk is re-read for every vocab block; the stash streams through once
       s.hint_a = kEvictFirst;
       s.hint_b = kEvictLast;
@@ -499,6 +553,11 @@ int grpo_set_option(const char* name, int value) {
   else if (!strcmp(name, "l2_hints")) g_knobs.l2_hints = value;
   else if (!strcmp(name, "dh_m_fast")) g_knobs.dh_m_fast = value;
   else if (!strcmp(name, "wait_hint_ns")) g_knobs.wait_hint_ns = value < 0 ? 0 : value;
+  else if (!strcmp(name, "epi_mode")) g_knobs.epi_mode = value & 3;
+  else if (!strcmp(name, "dw_tma")) g_knobs.dw_tma = value != 0;
+  else if (!strcmp(name, "st_hint")) g_knobs.st_hint = value & 3;
+  else if (!strcmp(name, "clk_probe")) g_knobs.clk_probe = value != 0;
+  else if (!strcmp(name, "acc_lead")) g_knobs.acc_lead = value < 0 ? 0 : value;
   else if (!strcmp(name, "chunk_rows")) g_knobs.chunk_rows = value > 0 ? (value + 511) / 512 * 512 : 0;
   else return fail(GRPO_ERR_ARG, "unknown option '%s'", name);
   return 0;
@@ -531,6 +590,9 @@ int grpo_profile_read(double* ms_out, long long* count_out, int reset) {
   return 0;
 }
 
+size_t grpo_debug_probe_offset(int64_t rows, int64_t hidden_dim, int64_t vocab, int with_stash) {
+  return carve(nullptr, rows, hidden_dim, vocab, with_stash != 0).probe_offset;
+}
 size_t grpo_lmhead_fwd_workspace_bytes(int64_t rows, int64_t hidden_dim, int64_t vocab) {
   return carve(nullptr, rows, hidden_dim, vocab, false).bytes;
 }
@@ -844,10 +906,19 @@ int grpo_debug_gemm(const void* a, const void* b, float* c, int64_t m, int64_t n
   DevInfo dev;
   GRPO_TRY(get_dev(&dev));
   dev.cta_group = cta_group;  // explicit for the debug entry; the tile shape (ksub) follows the process-wide knob
-  EpiF32<1, kBlockN>::Params p1{c, n, static_cast<uint32_t>(m), static_cast<uint32_t>(n),
-                                static_cast<uint32_t>(accumulate != 0)};
-  EpiF32<2, kBlockN>::Params p2{c, n, static_cast<uint32_t>(m), static_cast<uint32_t>(n),
-                                static_cast<uint32_t>(accumulate != 0)};
+  EpiF32<1, kBlockN>::Params p1;
+  memset(&p1, 0, sizeof(p1));
+  p1.c = c;
+  p1.ldc = n;
+  p1.m = static_cast<uint32_t>(m);
+  p1.n = static_cast<uint32_t>(n);
+  p1.accumulate = static_cast<uint32_t>(accumulate != 0);
+  p1.policy = kEvictNormal;
+  p1.use_tma = dev.dw_tma ? 1u : 0u;  // the debug entry exercises whichever fp32 epilogue the process-wide knob selects
+  if (p1.use_tma) GRPO_TRY(make_tmap_f32_out(&p1.c_map, c, static_cast<uint64_t>(n), static_cast<uint64_t>(m),
+                                             static_cast<uint64_t>(n)));
+  EpiF32<2, kBlockN>::Params p2;
+  memcpy(&p2, &p1, sizeof(p1));
   TileSched s{};
   s.m_fast = 1;
   // A: 0 = [m][k], 1 = [k][m], 2 = blocked [m/64][k/64][64][64], 3 = blocked [k/64][m/64][64 k][64 m]

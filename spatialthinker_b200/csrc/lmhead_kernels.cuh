@@ -53,7 +53,8 @@ __global__ void label_dot_kernel(const __nv_bfloat16* __restrict__ hidden, const
 // ------------------------------------------------------------------------------------------
 template <int kCta, int BLOCK_N>
 struct EpiSoftmax {
-  struct Params {
+  struct alignas(64) Params {
+    CUtensorMap stash_map;  // store map over the blocked stash, box (64 cols, 32 rows, 1, 1), SWIZZLE_128B; iff mode & 2
     uint32_t rows;       // token rows in this launch
     uint32_t vocab;      // V
     uint32_t rows_pad;   // leading dimension of the partial arrays
@@ -63,11 +64,90 @@ struct EpiSoftmax {
     float* part_ez;      // [n_tiles][rows_pad]  sum_v exp(z - z_label) * z      (nullptr: skip)
     __nv_bfloat16* stash;   // blocked [rows/64][stash_vb][64][64]: exp(z - z_label) in bf16 (nullptr: forward only)
     uint32_t stash_vb;      // 64-column blocks per row block
+    // bit 0: full tiles drain TMEM software-pipelined (the load of column group g+1 is in flight while g is processed)
+    // bit 1: (with bit 0) the stash leaves through shared memory and bulk tensor stores, 4 KB per warp and 64 columns,
+    //        instead of 16-byte st.global.cs pieces in 32 different 128-byte lines per warp instruction
+    uint32_t mode;
+    uint64_t policy;  // L2 eviction priority of the stash stores: it is next read by another kernel, after 5.8 GB went by
   };
-  static constexpr int kSmemBytes = 0;
+  static constexpr int kSmemBytes = 8 * kEpiStageBytes;
+  __device__ static void finish(const Params& p, uint32_t lane) {
+    if ((p.mode & 2) && lane == 0) bulk_wait_all();
+  }
+
+  // One 32-column group of a full tile: exponentials, running sums, bf16 pack; the packed row piece goes either to the
+  // warp's staging buffer (swizzled 16-byte chunks `chunk0 .. chunk0+3` of this thread's 128-byte row) or to global.
+  template <bool kWantEz>
+  __device__ static __forceinline__ void group_full(const uint32_t (&v)[32], float c1, float off, float& s0, float& s1,
+                                                    float& t0, float& t1, bool want_stash, uint8_t* smem_row,
+                                                    uint32_t sw, uint32_t chunk0, __nv_bfloat16* gdst) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float e[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) e[i] = fast_exp2(fminf(fmaf(__uint_as_float(v[8 * q + i]), c1, -off), kClampLog2));
+#pragma unroll
+      for (int i = 0; i < 8; i += 2) {
+        s0 += e[i];
+        s1 += e[i + 1];
+      }
+      if (kWantEz) {
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) {
+          t0 = fmaf(e[i], __uint_as_float(v[8 * q + i]), t0);
+          t1 = fmaf(e[i + 1], __uint_as_float(v[8 * q + i + 1]), t1);
+        }
+      }
+      if (want_stash) {
+        const uint32_t x = pack_bf16x2(e[0], e[1]), y = pack_bf16x2(e[2], e[3]);
+        const uint32_t z = pack_bf16x2(e[4], e[5]), w = pack_bf16x2(e[6], e[7]);
+        if (smem_row) st_shared_v4(smem_row + (((chunk0 + q) ^ sw) << 4), x, y, z, w);
+        else __stcs(reinterpret_cast<uint4*>(gdst + q * 8), make_uint4(x, y, z, w));
+      }
+    }
+  }
+
+  template <bool kWantEz, class Release>
+  __device__ static __forceinline__ void run_full(const Params& p, const EpiCtx& c, uint8_t* smem_epi, Release&& release,
+                                                  float c1, float off, __nv_bfloat16* srow, float& s0, float& s1,
+                                                  float& t0, float& t1) {
+    const bool want_stash = p.stash != nullptr;
+    const bool via_tma = want_stash && (p.mode & 2);
+    uint8_t* buf = smem_epi + c.epi_warp * kEpiStageBytes;
+    uint8_t* smem_row = via_tma ? buf + c.lane * 128 : nullptr;
+    const uint32_t sw = c.lane & 7;
+    const int32_t rb = static_cast<int32_t>(c.row0 >> 6), r_in = static_cast<int32_t>(c.row0 & 63);
+    const int32_t vb0 = static_cast<int32_t>(c.col0 >> 6);
+    uint32_t va[32], vb[32];
+    static_assert((BLOCK_N / 32) % 2 == 0, "column groups are drained in pairs (one 64-column stash block)");
+    tmem_ld_32x32(c.tmem_acc, va);
+#pragma unroll 1
+    for (int g = 0; g < BLOCK_N / 32; g += 2) {
+      tmem_ld_wait();
+      tmem_ld_32x32(c.tmem_acc + (g + 1) * 32, vb);
+      if (via_tma) {  // the previous 64-column block must have left the staging buffer
+        if (c.lane == 0) bulk_wait_read_all();
+        __syncwarp();
+      }
+      __nv_bfloat16* gdst = srow + (g >> 1) * 4096;
+      group_full<kWantEz>(va, c1, off, s0, s1, t0, t1, want_stash, smem_row, sw, 0, gdst);
+      tmem_ld_wait();
+      if (g + 2 < BLOCK_N / 32) tmem_ld_32x32(c.tmem_acc + (g + 2) * 32, va);
+      else release();  // last TMEM read of this accumulator has landed
+      group_full<kWantEz>(vb, c1, off, s0, s1, t0, t1, want_stash, smem_row, sw, 4, gdst + 32);
+      if (via_tma) {
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (c.lane == 0) {
+          tma_store_4d(&p.stash_map, buf, 0, r_in, vb0 + (g >> 1), rb, p.policy);
+          bulk_commit();
+        }
+      }
+    }
+  }
 
   template <class Release>
-  __device__ static void run(const Params& p, const EpiCtx& c, uint8_t*, Release&& release) {
+  __device__ static void run(const Params& p, const EpiCtx& c, uint8_t* smem_epi, Release&& release) {
     const uint32_t row = c.row, col0 = c.col0;
     const bool row_ok = row < p.rows;
     const uint32_t ncols = min(static_cast<uint32_t>(BLOCK_N), p.vocab - col0);
@@ -86,52 +166,57 @@ struct EpiSoftmax {
     const uint32_t store_groups = want_stash ? min(static_cast<uint32_t>(BLOCK_N / 32), 2 * (p.stash_vb - (col0 >> 6))) : 0;
 
     float s0 = 0.f, s1 = 0.f, t0 = 0.f, t1 = 0.f;
+    if ((p.mode & 1) && ncols == BLOCK_N) {  // every tile but the last one of the vocabulary
+      if (want_ez) run_full<true>(p, c, smem_epi, release, c1, off, srow, s0, s1, t0, t1);
+      else run_full<false>(p, c, smem_epi, release, c1, off, srow, s0, s1, t0, t1);
+    } else {
 #pragma unroll 1
-    for (uint32_t g = 0; g < ngroups; ++g) {
-      uint32_t v[32];
-      tmem_ld_32x32(c.tmem_acc + g * 32, v);
-      tmem_ld_wait();
-      if (g + 1 == ngroups) release();  // last TMEM read of this accumulator
-      const uint32_t valid = ncols - g * 32;  // >= 1
-      float e[32];
-      if (valid >= 32) {
+      for (uint32_t g = 0; g < ngroups; ++g) {
+        uint32_t v[32];
+        tmem_ld_32x32(c.tmem_acc + g * 32, v);
+        tmem_ld_wait();
+        if (g + 1 == ngroups) release();  // last TMEM read of this accumulator
+        const uint32_t valid = ncols - g * 32;  // >= 1
+        float e[32];
+        if (valid >= 32) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) e[i] = fast_exp2(fminf(fmaf(__uint_as_float(v[i]), c1, -off), kClampLog2));
-      } else {  // only the last group of the last vocabulary tile: zero-filled columns past the vocabulary
+          for (int i = 0; i < 32; ++i) e[i] = fast_exp2(fminf(fmaf(__uint_as_float(v[i]), c1, -off), kClampLog2));
+        } else {  // only the last group of the last vocabulary tile: zero-filled columns past the vocabulary
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          e[i] = static_cast<uint32_t>(i) < valid ? fast_exp2(fminf(fmaf(__uint_as_float(v[i]), c1, -off), kClampLog2)) : 0.f;
-      }
-#pragma unroll
-      for (int i = 0; i < 32; i += 2) {
-        s0 += e[i];
-        s1 += e[i + 1];
-      }
-      if (want_ez) {
+          for (int i = 0; i < 32; ++i)
+            e[i] = static_cast<uint32_t>(i) < valid ? fast_exp2(fminf(fmaf(__uint_as_float(v[i]), c1, -off), kClampLog2)) : 0.f;
+        }
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          t0 = fmaf(e[i], __uint_as_float(v[i]), t0);
-          t1 = fmaf(e[i + 1], __uint_as_float(v[i + 1]), t1);
+          s0 += e[i];
+          s1 += e[i + 1];
+        }
+        if (want_ez) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            t0 = fmaf(e[i], __uint_as_float(v[i]), t0);
+            t1 = fmaf(e[i + 1], __uint_as_float(v[i + 1]), t1);
+          }
+        }
+        if (want_stash) {
+          __nv_bfloat16* dst = srow + (g >> 1) * 4096 + (g & 1) * 32;  // 64-column block g/2, half g%2 of its 128-byte row
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 pk;
+            pk.x = pack_bf16x2(e[8 * q + 0], e[8 * q + 1]);
+            pk.y = pack_bf16x2(e[8 * q + 2], e[8 * q + 3]);
+            pk.z = pack_bf16x2(e[8 * q + 4], e[8 * q + 5]);
+            pk.w = pack_bf16x2(e[8 * q + 6], e[8 * q + 7]);
+            __stcs(reinterpret_cast<uint4*>(dst + q * 8), pk);  // streamed: keep the hidden panel in L2
+          }
         }
       }
-      if (want_stash) {
-        __nv_bfloat16* dst = srow + (g >> 1) * 4096 + (g & 1) * 32;  // 64-column block g/2, half g%2 of its 128-byte row
+      // column groups of the last vocabulary block that lie wholly past the vocabulary: zeros
+      for (uint32_t g = ngroups; g < store_groups; ++g) {
+        __nv_bfloat16* dst = srow + (g >> 1) * 4096 + (g & 1) * 32;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 pk;
-          pk.x = pack_bf16x2(e[8 * q + 0], e[8 * q + 1]);
-          pk.y = pack_bf16x2(e[8 * q + 2], e[8 * q + 3]);
-          pk.z = pack_bf16x2(e[8 * q + 4], e[8 * q + 5]);
-          pk.w = pack_bf16x2(e[8 * q + 6], e[8 * q + 7]);
-          __stcs(reinterpret_cast<uint4*>(dst + q * 8), pk);  // streamed: keep the hidden panel in L2
-        }
+        for (int q = 0; q < 4; ++q) __stcs(reinterpret_cast<uint4*>(dst + q * 8), make_uint4(0u, 0u, 0u, 0u));
       }
-    }
-    // column groups of the last vocabulary block that lie wholly past the vocabulary: zeros
-    for (uint32_t g = ngroups; g < store_groups; ++g) {
-      __nv_bfloat16* dst = srow + (g >> 1) * 4096 + (g & 1) * 32;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) __stcs(reinterpret_cast<uint4*>(dst + q * 8), make_uint4(0u, 0u, 0u, 0u));
     }
     if (row_ok) {
       const size_t o = static_cast<size_t>(c.n_blk) * p.rows_pad + row;

@@ -94,7 +94,7 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
 }
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // clears the CTA-pair rank bit of a shared::cluster address
 
-// L2 eviction-priority policies for TMA loads (the encodings CUTLASS' TMA::CacheHintSm90 uses).
+// L2 eviction-priority policies for TMA loads / stores (the encodings CUTLASS' TMA::CacheHintSm90 uses).
 constexpr uint64_t kEvictNormal = 0x1000000000000000ull;
 constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;  // streamed once: do not displace resident panels
 constexpr uint64_t kEvictLast = 0x14F0000000000000ull;   // re-read by every tile of the sweep: keep in L2
@@ -138,6 +138,36 @@ __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* ba
         "r"(c1), "r"(c2), "r"(c3), "l"(policy)
         : "memory");
   }
+}
+
+// ---- shared -> global bulk tensor stores (epilogues). The issuing thread owns a "bulk async-group": commit after the
+// copy, wait_group.read before the smem source is overwritten, wait_group before the kernel exits.
+// Generic-proxy writes (st.shared) must be made visible to the async proxy before the copy is issued.
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int32_t c0, int32_t c1,
+                                             int32_t c2, int32_t c3, uint64_t policy) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group.L2::cache_hint [%0, {%2, %3, %4, %5}], [%1], %6;"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3),
+                 "l"(policy)
+               : "memory");
+}
+// element-wise  global += smem  (the element type, fp32 here, comes from the tensor map); performed at L2
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, const void* src, int32_t c0, int32_t c1,
+                                                  uint64_t policy) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void st_shared_v4(void* dst, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(dst)), "r"(x), "r"(y), "r"(z), "r"(w)
+               : "memory");
 }
 
 // ------------------------------------------------------------------------------------------

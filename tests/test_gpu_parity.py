@@ -75,6 +75,69 @@ def test_debug_gemm_layouts(st, dev, cta, a_mn, b_mn):
     np.testing.assert_allclose(c.cpu().double().numpy(), (want + 3.0).numpy(), rtol=0, atol=2e-3)
 
 
+@pytest.mark.parametrize("accumulate", [0, 1])
+@pytest.mark.parametrize("tma", [0, 1])
+def test_debug_gemm_fp32_epilogues(st, dev, tma, accumulate):
+    """The fp32 epilogue through shared memory + bulk tensor store / reduce-add (the dW GEMM's) against the per-thread
+    st.global / red.global one, ragged edges in both dimensions (the TMA unit clips the boxes)."""
+    from spatialthinker_b200 import _lib
+
+    lib = _lib.load()
+    m, n, k = 1000, 520, 200
+    g = torch.Generator().manual_seed(11)
+    a = torch.randn(m, k, generator=g).to(torch.bfloat16)
+    b = torch.randn(n, k, generator=g).to(torch.bfloat16)
+    want = a.double() @ b.double().t() + (2.5 if accumulate else 0.0)
+    c = torch.full((m + 8, n), 2.5, device=dev)  # 8 guard rows: nothing may be written past row m
+    a_d, b_d = a.to(dev), b.to(dev)
+    _lib.check(lib.grpo_set_option(b"dw_tma", tma), "set_option")
+    try:
+        _lib.check(lib.grpo_debug_gemm(a_d.data_ptr(), b_d.data_ptr(), c.data_ptr(), m, n, k, 0, 0, 2,
+                                       accumulate, _lib.stream_ptr(dev)), "gemm")
+        torch.cuda.synchronize()
+    finally:
+        lib.grpo_set_option(b"dw_tma", 1)
+    np.testing.assert_allclose(c[:m].cpu().double().numpy(), want.numpy(), rtol=0, atol=2e-3)
+    assert bool((c[m:] == 2.5).all())
+
+
+def test_epilogue_variants_agree(st, dev):
+    """Softmax-epilogue variants (plain loop / pipelined TMEM drain / stash through bulk tensor stores) and dW-epilogue
+    variants must give the same log-probs bit for bit and the same gradients up to fp32 accumulation order."""
+    from spatialthinker_b200 import _lib
+
+    lib = _lib.load()
+    rows, h, v = 1100, 256, 2 * 4096 + 520  # several full vocab tiles + a ragged last one; rows ragged too
+    hid, w = O.synth_head(rows, h, v, seed=3, sigma_w=0.1)
+    g = torch.Generator().manual_seed(3)
+    lab = torch.randint(0, v, (rows,), generator=g)
+    gl = torch.randn(rows, generator=g) / rows
+    hf, wf = hid.float().requires_grad_(True), w.float().requires_grad_(True)
+    lp_ref, _ = O.lm_head_log_probs(hf, wf, lab, 1.0)
+    (lp_ref * gl).sum().backward()
+    outs = {}
+    try:
+        for epi, dwt, lead in ((0, 0, 0), (1, 0, 0), (3, 0, 1), (3, 1, 2), (0, 1, 3)):
+            _lib.check(lib.grpo_set_option(b"epi_mode", epi), "set_option")
+            _lib.check(lib.grpo_set_option(b"dw_tma", dwt), "set_option")
+            _lib.check(lib.grpo_set_option(b"acc_lead", lead), "set_option")
+            hd, wd = hid.to(dev).requires_grad_(True), w.to(dev).requires_grad_(True)
+            lp, _ = st.fused_lm_head_log_probs(hd, wd, lab.to(dev), 1.0)
+            (lp * gl.to(dev)).sum().backward()
+            outs[(epi, dwt, lead)] = (lp.detach().clone(), hd.grad.clone(), wd.grad.clone())
+    finally:
+        lib.grpo_set_option(b"epi_mode", 3)
+        lib.grpo_set_option(b"dw_tma", 1)
+        lib.grpo_set_option(b"acc_lead", 2)
+    base = outs[(0, 0, 0)]
+    assert float((base[0].cpu() - lp_ref.detach()).abs().max()) < TOL_LOGP
+    assert rel(base[1], hf.grad) < TOL_REL and rel(base[2], wf.grad) < TOL_REL
+    for key, (lp, dh, dw) in outs.items():
+        assert torch.equal(lp, base[0]), key
+        assert torch.equal(dh, base[1]), key  # same stash bits -> same dHidden bits
+        assert rel(dw, base[2]) < 1e-3, key  # bf16 grads: an fp32 ulp may flip a rounding
+
+
 # ================================================================================================ logits surface
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
 def test_log_probs_from_logits(st, dev, dtype):

@@ -44,7 +44,8 @@ for spec in args.variants:  # the workspace must fit the largest chunk setting a
     lib.grpo_set_option(b"chunk_rows", 0)
     lib.grpo_set_option(b"ksub", 2)
 ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-DEFAULTS = {"cta_group": 2, "fwd_panel": 4864, "sync_fwd": 28, "sync_dh": 8, "sync_dw": 8, "l2_hints": 0, "dh_m_fast": 0, "chunk_rows": 0, "ksub": 2, "wait_hint_ns": 10000000}
+DEFAULTS = {"cta_group": 2, "fwd_panel": 4864, "sync_fwd": 28, "sync_dh": 8, "sync_dw": 8, "l2_hints": 0, "dh_m_fast": 0, "chunk_rows": 0, "ksub": 2, "wait_hint_ns": 10000000,
+            "epi_mode": 3, "dw_tma": 1, "acc_lead": 2, "clk_probe": 1, "st_hint": 3}
 
 
 def apply(spec):
@@ -65,6 +66,9 @@ def bwd():
 for _ in range(3):
     bwd()
 torch.cuda.synchronize()
+probe_off = lib.grpo_debug_probe_offset(rows, h, v, 1)
+clk = {s: [[], [], []] for s in args.variants}  # GHz the three GEMMs really ran at (clock64 / globaltimer, last chunk)
+span = {s: [[], [], []] for s in args.variants}  # (kernel span, spread of group starts, spread of group ends) in ms
 res = {s: [] for s in args.variants}
 phases = {s: [0.0] * 6 for s in args.variants}
 lib.grpo_profile_enable(1)
@@ -81,6 +85,14 @@ for rnd in range(args.rounds):
         e1.record()
         torch.cuda.synchronize()
         res[spec].append(e0.elapsed_time(e1) / args.iters)
+        pr = ws[probe_off:probe_off + 3 * 2048].view(torch.int64).cpu().view(3, 256)
+        for i in range(3):
+            c0, n0, c1, n1 = pr[i, :4].tolist()
+            if n1 > n0:
+                clk[spec][i].append((c1 - c0) / (n1 - n0))
+            g = pr[i, 8:8 + 2 * 74].view(74, 2)
+            span[spec][i].append(((g[:, 1].max() - g[:, 0].min()).item() / 1e6, (g[:, 0].max() - g[:, 0].min()).item() / 1e6,
+                                  (g[:, 1].max() - g[:, 1].min()).item() / 1e6))
         ms = (ctypes.c_double * 6)()
         cnt = (ctypes.c_longlong * 6)()
         lib.grpo_profile_read(ms, cnt, 1)
@@ -91,4 +103,7 @@ for spec in args.variants:
     t = res[spec]
     med = statistics.median(t)
     ph = "  ".join(f"{n}={phases[spec][i]:.3f}" for i, n in enumerate(_lib.PHASE_NAMES))
+    ghz = " ".join(f"{statistics.median(c):.3f}" if c else "-" for c in clk[spec])
+    ph += f" | GHz fwd/dh/dw {ghz} | span/start-spread/end-spread ms " + " ".join(
+        "/".join(f"{statistics.median(x[j] for x in sp):.3f}" for j in range(3)) if sp else "-" for sp in span[spec])
     print(f"[{spec or 'default':28s}] median {med:7.3f} ms  min {min(t):7.3f}  max {max(t):7.3f}  -> {3 * unit / med / 1e9:6.0f} TF alg | {ph}")
