@@ -158,6 +158,25 @@ int grpo_advantage_from_scores(const float* scores_all, const int32_t* order, co
                                grpo_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * Ragged micro-batches: run the head on the unmasked response slots only.
+ * Replaces: the reference computes log-probs for every slot of the padded [B, T] block and multiplies the padded ones
+ * by zero (dp_actor.py:136-139, :253-273); its padding-free branch gathers / scatters tokens for the transformer body
+ * only (flash-attn bert_padding unpad_input / pad_input, dp_actor.py:86-104).
+ *   grpo_compact_index: gather_idx int32 [n] (gather_idx[j] = slot of the j-th unmasked entry, original order; entries
+ *     past the count are unspecified), inverse int32 [n] (inverse[slot] = j or -1), count int32 [1] (device),
+ *     scratch of grpo_compact_scratch_bytes(n). mask_dtype 0..2. No host synchronisation.
+ *   grpo_gather_rows : out[j][:] = in[gather_idx[j]][:] for j < m           (rows of row_bytes bytes, multiple of 4)
+ *   grpo_scatter_rows: out[i][:] = inverse[i] >= 0 ? in[inverse[i]][:] : 0   for i < n   (every output row written)
+ * ------------------------------------------------------------------------------------------------------------------ */
+size_t grpo_compact_scratch_bytes(int64_t n);
+int grpo_compact_index(const void* mask, int mask_dtype, int64_t n, int32_t* gather_idx, int32_t* inverse,
+                       int32_t* count, void* scratch, size_t scratch_bytes, grpo_stream_t stream);
+int grpo_gather_rows(const void* in, const int32_t* gather_idx, int64_t m, int64_t row_bytes, void* out,
+                     grpo_stream_t stream);
+int grpo_scatter_rows(const void* in, const int32_t* inverse, int64_t n, int64_t row_bytes, void* out,
+                      grpo_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * log_probs_from_logits on MATERIALISED logits (torch_functional.py:45-66), API parity only.
  *   logits_dtype: 0 = f32, 1 = bf16, 2 = f16;  logits [rows][ld];  logp / entropy / lse f32 [rows] (each nullable)
  * Backward: dlogits = dlogp * (onehot - softmax) - dentropy * p * (log p + H)   (dlogits may alias logits).

@@ -51,6 +51,10 @@ _SIGNATURES = {
     "grpo_advantage": (c_int, [_P, _P, c_int, _P, _P, c_int64, c_int64, c_int64, c_float, _P, _P, _P]),
     "grpo_sequence_scores": (c_int, [_P, c_int64, c_int64, _P, _P]),
     "grpo_advantage_from_scores": (c_int, [_P, _P, _P, c_int64, c_int64, c_float, c_int64, _P, c_int, c_int64, c_int64, _P, _P, _P]),
+    "grpo_compact_scratch_bytes": (c_size_t, [c_int64]),
+    "grpo_compact_index": (c_int, [_P, c_int, c_int64, _P, _P, _P, _P, c_size_t, _P]),
+    "grpo_gather_rows": (c_int, [_P, _P, c_int64, c_int64, _P, _P]),
+    "grpo_scatter_rows": (c_int, [_P, _P, c_int64, c_int64, _P, _P]),
     "grpo_logprob_from_logits": (c_int, [_P, c_int, _P, c_int64, c_int64, c_int64, _P, _P, _P, _P]),
     "grpo_logprob_from_logits_bwd": (c_int, [_P, c_int, _P, _P, _P, _P, _P, c_int64, c_int64, c_int64, _P, c_int64, _P]),
     "grpo_debug_gemm": (c_int, [_P, _P, _P, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_int, _P]),

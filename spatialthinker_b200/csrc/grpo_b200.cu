@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "advantage_kernels.cuh"
+#include "compact_kernels.cuh"
 #include "gemm_core.cuh"
 #include "lmhead_kernels.cuh"
 #include "logits_kernels.cuh"
@@ -220,6 +221,7 @@ static void init_knobs() {
     g_knobs.epi_mode = env_int("GRPO_EPI_MODE", g_knobs.epi_mode) & 3;
     g_knobs.dw_tma = env_int("GRPO_DW_TMA", g_knobs.dw_tma) != 0;
     g_knobs.acc_lead = env_int("GRPO_ACC_LEAD", g_knobs.acc_lead);
+    g_knobs.st_hint = env_int("GRPO_ST_HINT", g_knobs.st_hint) & 3;
   });
 }
 
@@ -826,6 +828,84 @@ int grpo_advantage(const float* rewards, const void* mask, int mask_dtype, const
   count_launch();
   broadcast_adv_kernel<<<ew_blocks(bsz * t_len, 256, 0), 256, 0, stream>>>(seq_adv, mask, mask_dtype, b, t,
                                                                            advantages);
+  count_launch();
+  GRPO_CUDA(cudaGetLastError());
+  return 0;
+}
+
+size_t grpo_compact_scratch_bytes(int64_t n) {
+  return n <= 0 ? sizeof(int32_t) : (static_cast<size_t>((n + kCompactBlock - 1) / kCompactBlock) + 1) * sizeof(int32_t);
+}
+
+int grpo_compact_index(const void* mask, int mask_dtype, int64_t n, int32_t* gather_idx, int32_t* inverse,
+                       int32_t* count, void* scratch, size_t scratch_bytes, grpo_stream_t stream) {
+  if (!mask || !gather_idx || !inverse || !count || !scratch)
+    return fail(GRPO_ERR_ARG, "mask / gather_idx / inverse / count / scratch must not be null");
+  if (mask_dtype < 0 || mask_dtype > 2) return fail(GRPO_ERR_ARG, "bad mask_dtype");
+  if (n < 0 || n > 0x7fffffffll) return fail(GRPO_ERR_ARG, "bad length");
+  if (scratch_bytes < grpo_compact_scratch_bytes(n)) return fail(GRPO_ERR_WORKSPACE, "compaction scratch too small");
+  auto* blocks = static_cast<int32_t*>(scratch);
+  const uint32_t nb = cdiv(n, kCompactBlock);
+  if (nb > 0) {
+    compact_count_kernel<<<nb, kCompactThreads, 0, stream>>>(mask, mask_dtype, static_cast<size_t>(n), blocks);
+    count_launch();
+  }
+  compact_scan_kernel<<<1, 1024, 0, stream>>>(blocks, nb, count);
+  count_launch();
+  if (nb > 0) {
+    compact_write_kernel<<<nb, kCompactThreads, 0, stream>>>(mask, mask_dtype, static_cast<size_t>(n), blocks,
+                                                             gather_idx, inverse);
+    count_launch();
+  }
+  GRPO_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int check_rows_args(const void* in, const int32_t* idx, void* out, int64_t n, int64_t row_bytes) {
+  if (!in || !idx || !out) return fail(GRPO_ERR_ARG, "in / index / out must not be null");
+  if (n < 0 || n > 0x7fffffffll || row_bytes <= 0 || row_bytes % 4 != 0 || row_bytes > (1ll << 30))
+    return fail(GRPO_ERR_ARG, "bad row count / row_bytes (must be a positive multiple of 4)");
+  return 0;
+}
+static inline bool rows_vec16(const void* in, const void* out, int64_t row_bytes) {
+  return row_bytes % 16 == 0 && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0;
+}
+static inline uint32_t rows_grid(int64_t rows, uint32_t vecs_per_row) {
+  if (vecs_per_row >= 32) return cdiv(rows * 32, 256);
+  return ew_blocks(rows * vecs_per_row, 256, 0);
+}
+
+int grpo_gather_rows(const void* in, const int32_t* gather_idx, int64_t m, int64_t row_bytes, void* out,
+                     grpo_stream_t stream) {
+  GRPO_TRY(check_rows_args(in, gather_idx, out, m, row_bytes));
+  if (m == 0) return 0;
+  if (rows_vec16(in, out, row_bytes)) {
+    const uint32_t vpr = static_cast<uint32_t>(row_bytes / 16);
+    gather_rows_kernel<uint4><<<rows_grid(m, vpr), 256, 0, stream>>>(
+        static_cast<const uint4*>(in), gather_idx, static_cast<size_t>(m), vpr, static_cast<uint4*>(out));
+  } else {
+    const uint32_t vpr = static_cast<uint32_t>(row_bytes / 4);
+    gather_rows_kernel<uint32_t><<<rows_grid(m, vpr), 256, 0, stream>>>(
+        static_cast<const uint32_t*>(in), gather_idx, static_cast<size_t>(m), vpr, static_cast<uint32_t*>(out));
+  }
+  count_launch();
+  GRPO_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int grpo_scatter_rows(const void* in, const int32_t* inverse, int64_t n, int64_t row_bytes, void* out,
+                      grpo_stream_t stream) {
+  GRPO_TRY(check_rows_args(in, inverse, out, n, row_bytes));
+  if (n == 0) return 0;
+  if (rows_vec16(in, out, row_bytes)) {
+    const uint32_t vpr = static_cast<uint32_t>(row_bytes / 16);
+    scatter_rows_kernel<uint4><<<rows_grid(n, vpr), 256, 0, stream>>>(
+        static_cast<const uint4*>(in), inverse, static_cast<size_t>(n), vpr, static_cast<uint4*>(out));
+  } else {
+    const uint32_t vpr = static_cast<uint32_t>(row_bytes / 4);
+    scatter_rows_kernel<uint32_t><<<rows_grid(n, vpr), 256, 0, stream>>>(
+        static_cast<const uint32_t*>(in), inverse, static_cast<size_t>(n), vpr, static_cast<uint32_t*>(out));
+  }
   count_launch();
   GRPO_CUDA(cudaGetLastError());
   return 0;

@@ -14,6 +14,7 @@ the final hidden states and the ``lm_head`` weight instead:
 """
 from __future__ import annotations
 
+import math
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -204,30 +205,73 @@ def grpo_micro_batch_step(
     }
 
 
+def compact_index(response_mask: torch.Tensor):
+    """(gather_idx, inverse, count) of the unmasked slots of ``response_mask`` (flattened), built on the device by
+    ``grpo_compact_index`` - stable order, no host synchronisation. ``count`` is a 1-element int32 device tensor."""
+    dev = require_cuda(response_mask)
+    lib = _lib.load()
+    mask, code = mask_arg(response_mask)
+    n = mask.numel()
+    gather_idx = torch.empty(n, dtype=torch.int32, device=dev)
+    inverse = torch.empty(n, dtype=torch.int32, device=dev)
+    count = torch.empty(1, dtype=torch.int32, device=dev)
+    nbytes = lib.grpo_compact_scratch_bytes(n)
+    tmp = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.grpo_compact_index(mask.data_ptr(), code, n, gather_idx.data_ptr(), inverse.data_ptr(),
+                                          count.data_ptr(), tmp.data_ptr(), nbytes, _lib.stream_ptr(dev)),
+                   "grpo_compact_index")
+    return gather_idx, inverse, count
+
+
+def gather_rows(src: torch.Tensor, gather_idx: torch.Tensor, m: int) -> torch.Tensor:
+    """``out[j] = src[gather_idx[j]]`` for ``j < m`` over the leading dimension (``grpo_gather_rows``)."""
+    dev = require_cuda(src, gather_idx)
+    src = src.contiguous()
+    row_bytes = math.prod(src.shape[1:]) * src.element_size()
+    out = torch.empty((m,) + tuple(src.shape[1:]), dtype=src.dtype, device=dev)
+    if m == 0:
+        return out
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().grpo_gather_rows(src.data_ptr(), gather_idx.data_ptr(), m, row_bytes, out.data_ptr(),
+                                                _lib.stream_ptr(dev)), "grpo_gather_rows")
+    return out
+
+
+def scatter_rows(src: torch.Tensor, inverse: torch.Tensor) -> torch.Tensor:
+    """``out[i] = src[inverse[i]]`` where ``inverse[i] >= 0``, zeros elsewhere (``grpo_scatter_rows``)."""
+    dev = require_cuda(src, inverse)
+    src = src.contiguous()
+    n = inverse.numel()
+    row_bytes = math.prod(src.shape[1:]) * src.element_size()
+    if src.shape[0] == 0 or n == 0:  # nothing was kept: all zeros
+        return torch.zeros((n,) + tuple(src.shape[1:]), dtype=src.dtype, device=dev)
+    out = torch.empty((n,) + tuple(src.shape[1:]), dtype=src.dtype, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().grpo_scatter_rows(src.data_ptr(), inverse.data_ptr(), n, row_bytes, out.data_ptr(),
+                                                 _lib.stream_ptr(dev)), "grpo_scatter_rows")
+    return out
+
+
 def _compacted_step(hidden, weight, labels, old_log_probs, advantages, ref_log_probs, response_mask, valid_rows, kw):
-    """Gather the ``valid_rows`` unmasked token rows, run the fused step on them, scatter the results back."""
+    """Gather the ``valid_rows`` unmasked token rows, run the fused step on them, scatter the results back (padded slots
+    get zeros). Index, gather and scatter are this library's kernels (csrc/compact_kernels.cuh); the count comes from the
+    host, so nothing synchronises."""
     lead = hidden.shape[:-1]
     hdim = hidden.shape[-1]
-    flat_mask = response_mask.reshape(-1)
-    # stable sort puts the unmasked rows first, in their original order; the count is known on the host: no sync
-    order = torch.argsort((flat_mask != 0).to(torch.int8), descending=True, stable=True)
-    idx = order[:valid_rows]
-    take = lambda t: None if t is None else t.reshape(-1).index_select(0, idx)  # noqa: E731
+    gather_idx, inverse, _ = compact_index(response_mask)
+    take = lambda t: None if t is None else gather_rows(t.reshape(-1), gather_idx, valid_rows)  # noqa: E731
+    mask_flat = response_mask.reshape(-1)
+    if mask_flat.element_size() % 4 != 0:  # bool / uint8 masks: the row kernels move 4-byte words
+        mask_flat = mask_flat.to(torch.float32)
     res = grpo_micro_batch_step(
-        hidden.reshape(-1, hdim).index_select(0, idx), weight, take(labels), take(old_log_probs), take(advantages),
-        take(ref_log_probs), take(flat_mask), **kw)
-    dev = hidden.device
-    logp = torch.zeros(flat_mask.numel(), dtype=torch.float32, device=dev)
-    logp.index_copy_(0, idx, res["log_probs"])
-    res["log_probs"] = logp.view(*lead)
+        gather_rows(hidden.reshape(-1, hdim), gather_idx, valid_rows), weight, take(labels), take(f32c(old_log_probs)),
+        take(f32c(advantages)), take(None if ref_log_probs is None else f32c(ref_log_probs)), take(mask_flat), **kw)
+    res["log_probs"] = scatter_rows(res["log_probs"], inverse).view(*lead)
     if res["entropy"] is not None:
-        ent = torch.zeros(flat_mask.numel(), dtype=torch.float32, device=dev)
-        ent.index_copy_(0, idx, res["entropy"])
-        res["entropy"] = ent.view(*lead)
+        res["entropy"] = scatter_rows(res["entropy"], inverse).view(*lead)
     if res["dhidden"] is not None:
-        dh = torch.zeros(flat_mask.numel(), hdim, dtype=torch.bfloat16, device=dev)
-        dh.index_copy_(0, idx, res["dhidden"])
-        res["dhidden"] = dh.view(hidden.shape)
+        res["dhidden"] = scatter_rows(res["dhidden"], inverse).view(hidden.shape)
     return res
 
 

@@ -85,6 +85,7 @@ for rnd in range(args.rounds):
         e1.record()
         torch.cuda.synchronize()
         res[spec].append(e0.elapsed_time(e1) / args.iters)
+        probe_off = lib.grpo_debug_probe_offset(rows, h, v, 1)  # depends on the variant's chunk size
         pr = ws[probe_off:probe_off + 3 * 2048].view(torch.int64).cpu().view(3, 256)
         for i in range(3):
             c0, n0, c1, n1 = pr[i, :4].tolist()
