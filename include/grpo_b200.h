@@ -65,7 +65,7 @@ long long grpo_launch_count(void);
  * "sync_dw" progress-barrier periods in K-blocks (0 = off), "l2_hints" 0|1. Defaults are the measured configuration. */
 int grpo_set_option(const char* name, int value);
 /* Measurement aid: with option "clk_probe" = 1 the three GEMM kernels of the chunk pipeline write
- * 256 x uint64 each (order logits / dHidden / dW) at this byte offset of the caller's workspace:
+ * 1024 x uint64 each (order logits / dHidden / dW) at this byte offset of the caller's workspace:
  * [0..3] = block 0 {clock64 at entry, globaltimer ns at entry, clock64 at exit, globaltimer ns at exit} (cycles / ns = the
  * SM clock the kernel really ran at), [8 + 2g], [9 + 2g] = entry / exit ns of persistent CTA group g. */
 size_t grpo_debug_probe_offset(int64_t rows, int64_t hidden_dim, int64_t vocab, int with_stash);

@@ -11,7 +11,9 @@ from ctypes import c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgrpo_b200.so")
+# GRPO_B200_LIB: measurement tooling only (e.g. the -DGRPO_TRACE build of tools/trace_tiles.py); the product loads the
+# in-tree library
+LIB_PATH = os.environ.get("GRPO_B200_LIB") or os.path.join(_HERE, "libgrpo_b200.so")
 
 # keep in sync with include/grpo_b200.h
 KL_MODES = {None: -1, "none": -1, "low_var_kl": 0, "kl": 1, "abs": 2, "mse": 3, "chi2": 4}

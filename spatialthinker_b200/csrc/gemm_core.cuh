@@ -92,6 +92,23 @@ __device__ __forceinline__ void decode_tile(const TileSched& s, uint32_t t, uint
   }
 }
 
+// Build with -DGRPO_TRACE (tools/trace_tiles.py; never the product build) to have CTA 0 log clock64 at the pipeline
+// events of its first 16 tiles into the probe area: [256 + 16 * event + tile].
+//   0/1 first MMA of accumulator 0/1 issued   2/3 last MMA of accumulator 0/1 issued
+//   4/5 epilogue 0/1 saw its accumulator complete   6/7 epilogue 0/1 released its TMEM slot   8/9 epilogue 0/1 done
+//   10  producer issued the tile's first load
+#ifdef GRPO_TRACE
+#define GRPO_TR(ev, tile)                                                                        \
+  do {                                                                                           \
+    if (sched.probe != nullptr && blockIdx.x == 0 && (tile) < 16u)                               \
+      sched.probe[256 + 16 * (ev) + (tile)] = static_cast<unsigned long long>(clock64());        \
+  } while (0)
+#else
+#define GRPO_TR(ev, tile) \
+  do {                    \
+  } while (0)
+#endif
+
 // What an epilogue sees for one 128 x BLOCK_N accumulator.
 struct EpiCtx {
   uint32_t row;       // global output row owned by this thread (TMEM lane)
@@ -210,6 +227,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           if (do_sync && progress != 0 && progress % sched.sync_period == 0)
             progress_sync(sched.sync_ctr, ++rounds_done, tile_step, give_up);
           mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (kb == 0) GRPO_TR(10, (t - first_tile) / tile_step);
           const int32_t k0 = static_cast<int32_t>(kb * kBlockK);
           uint8_t* sa = smem_a + stage * Cfg::kABytes;
           uint8_t* sb = smem_b + stage * Cfg::kBBytes;
@@ -267,13 +285,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           }
           const uint32_t a_addr = smem_u32(smem_a + stage * Cfg::kABytes);
           const uint32_t b_addr = smem_u32(smem_b + stage * Cfg::kBBytes);
+          if (kb == 0) GRPO_TR(sub, it);
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
             const uint64_t da = make_smem_desc(a_addr + sub * a_sub + k * a_kstep, 1024, a_lbo);
             const uint64_t db = make_smem_desc(b_addr + k * b_kstep, 1024, b_lbo);
             umma_bf16<kCta>(tmem_base + (slot0 + sub) * BLOCK_N, da, db, idesc, (kb | k) != 0);
           }
-          if (kb + 1 == kblocks) umma_commit<kCta>(&tmem_full[slot0 + sub]);  // this accumulator is complete
+          if (kb + 1 == kblocks) {
+            umma_commit<kCta>(&tmem_full[slot0 + sub]);  // this accumulator is complete
+            GRPO_TR(2 + sub, it);
+          }
         };
         // frees the smem slot of K-block `kb` (both CTAs) when the MMAs issued so far retire
         auto free_stage = [&](uint32_t kb) { umma_commit<kCta>(&empty_bar[(base + kb) % kStages]); };
@@ -337,14 +359,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       c.tmem_acc = tmem_base + slot * BLOCK_N + ((quad * 32u) << 16);
       mbar_wait(&tmem_full[slot], ap, sched.wait_hint_ns);
       tc_fence_after();
+      if (quad == 0 && lane == 0) GRPO_TR(4 + (slot & 1), it);
       // the epilogue calls `release` as soon as its last TMEM load has completed, before it finishes the arithmetic
       // and the stores of that last column group: the MMA warp can refill the slot that much earlier
       auto release = [&]() {
         tc_fence_before();
         if (leader) mbar_arrive(&tmem_empty[slot]);
         else mbar_arrive_cluster(&tmem_empty[slot], 0);
+        if (quad == 0 && lane == 0) GRPO_TR(6 + (slot & 1), it);
       };
       Epi::run(ep, c, smem_epi, release);
+      if (quad == 0 && lane == 0) GRPO_TR(8 + (slot & 1), it);
     }
     Epi::finish(ep, lane);  // outstanding bulk stores of this warp
   }

@@ -126,23 +126,24 @@ static int make_tmap_bf16(CUtensorMap* map, const void* base, uint64_t inner, ui
 
 // Blocked bf16 operand [blk3][blk2][64][64] (64 x 64 blocks of 8 KB, inner row = 128 B); box = (64, 64, box2, box3).
 static int make_tmap_blocked(CUtensorMap* map, const void* base, uint64_t n_blk2, uint64_t n_blk3, uint64_t blk3_pitch,
-                             uint32_t box2, uint32_t box3, uint32_t box_rows = 64) {
+                             uint32_t box2, uint32_t box3, uint32_t box_rows = 64, uint32_t box_cols = 64) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail(GRPO_ERR_DRIVER, "cuTensorMapEncodeTiled entry point not available");
   if (reinterpret_cast<uintptr_t>(base) & 15u) return fail(GRPO_ERR_ARG, "TMA operand must be 16-byte aligned");
   const cuuint64_t dims[4] = {64, 64, n_blk2, n_blk3};
   const cuuint64_t strides[3] = {128, 8192, blk3_pitch * 8192};
-  const cuuint32_t box[4] = {64, box_rows, box2, box3};
+  const cuuint32_t box[4] = {box_cols, box_rows, box2, box3};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(GRPO_ERR_DRIVER, "cuTensorMapEncodeTiled (blocked) failed with CUresult %d", (int)r);
   return 0;
 }
 
 // fp32 matrix [rows][cols] (row pitch `pitch_elems`), box 32 x 32 (128-byte rows, 128-byte swizzle): the epilogue's
-// bulk store / reduce-add target.
+// bulk store / reduce-add target. (Two 16-column boxes per group out of alternating staging halves were measured
+// slower: the reduce-adds of all CTAs arrive together and are bound by L2 atomic throughput, ~5.6 TB/s.)
 static int make_tmap_f32_out(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, uint64_t pitch_elems) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail(GRPO_ERR_DRIVER, "cuTensorMapEncodeTiled entry point not available");
@@ -193,8 +194,8 @@ struct Knobs {
   int chunk_rows = 0;  // rows per chunk of the pipeline (0: 37 row tiles, see default_chunk_rows)
   int wait_hint_ns = 10000000;  // suspend hint of the epilogue warps' accumulator-ready wait (0: busy poll)
   // softmax epilogue of the logits GEMM, bit 0: software-pipelined TMEM drain, bit 1: exp-stash through shared memory +
-  // bulk tensor stores (EpiSoftmax::Params::mode)
-  int epi_mode = 3;
+  // bulk tensor stores, bit 2: 2 KB staging halves (EpiSoftmax::Params::mode)
+  int epi_mode = 7;
   int acc_lead = 2;    // wide tile: accumulator 0's lead over accumulator 1 at the tile ends, in K-blocks (TileSched::acc_lead)
   int st_hint = 3;     // bit 0: stash bulk stores evict-first, bit 1: dW bulk reduce-adds evict-first (else normal)
   int clk_probe = 0;   // 1: the GEMM kernels record clock64 / globaltimer at entry and exit (grpo_debug_probe_offset)
@@ -218,7 +219,7 @@ static void init_knobs() {
     g_knobs.dh_m_fast = env_int("GRPO_DH_M_FAST", g_knobs.dh_m_fast);
     g_knobs.chunk_rows = env_int("GRPO_CHUNK_ROWS", g_knobs.chunk_rows);
     g_knobs.wait_hint_ns = env_int("GRPO_WAIT_HINT_NS", g_knobs.wait_hint_ns);
-    g_knobs.epi_mode = env_int("GRPO_EPI_MODE", g_knobs.epi_mode) & 3;
+    g_knobs.epi_mode = env_int("GRPO_EPI_MODE", g_knobs.epi_mode) & 7;
     g_knobs.dw_tma = env_int("GRPO_DW_TMA", g_knobs.dw_tma) != 0;
     g_knobs.acc_lead = env_int("GRPO_ACC_LEAD", g_knobs.acc_lead);
     g_knobs.st_hint = env_int("GRPO_ST_HINT", g_knobs.st_hint) & 3;
@@ -327,7 +328,7 @@ struct Workspace {
   float *row_scale = nullptr, *onehot = nullptr;
   double* acc = nullptr;
   uint32_t* sync = nullptr;  // progress-barrier counters, one per GEMM of the chunk pipeline (first 64 bytes)
-  unsigned long long* probe = nullptr;  // clock probes of the three GEMMs, 256 x u64 each (measurement aid)
+  unsigned long long* probe = nullptr;  // clock probes of the three GEMMs, 1024 x u64 each (measurement aid)
   size_t probe_offset = 0;
   size_t bytes = 0;
 };
@@ -367,7 +368,7 @@ static Workspace carve(void* base, int64_t rows, int64_t hdim, int64_t vocab, bo
   w.onehot = reinterpret_cast<float*>(take(vec));
   w.acc = reinterpret_cast<double*>(take(ACC_N * sizeof(double)));
   w.probe_offset = off + 64;
-  w.sync = reinterpret_cast<uint32_t*>(take(64 + 3 * 2048));
+  w.sync = reinterpret_cast<uint32_t*>(take(64 + 3 * 8192));
   w.probe = p ? reinterpret_cast<unsigned long long*>(p + w.probe_offset) : nullptr;
   w.bytes = off;
   return w;
@@ -402,9 +403,13 @@ static int chunk_forward(const DevInfo& dev, const Workspace& w, const __nv_bflo
   p1.mode = static_cast<uint32_t>(dev.epi_mode);
   p1.policy = (dev.st_hint & 1) ? kEvictFirst : kEvictNormal;
   if (!want_stash || !(p1.mode & 1)) p1.mode &= 1u;
+  if (!(p1.mode & 2)) p1.mode &= 3u;
   if (p1.mode & 2)  // store view of the blocked stash: 32 rows x 64 columns (4 KB, contiguous in HBM) per bulk store
     GRPO_TRY(make_tmap_blocked(&p1.stash_map, w.stash, static_cast<uint64_t>(w.stash_vb),
                                static_cast<uint64_t>(w.rows_pad / 64), static_cast<uint64_t>(w.stash_vb), 1, 1, 32));
+  if (p1.mode & 4)  // ... or 32 rows x 32 columns (64-byte pieces of 32 consecutive 128-byte rows) per bulk store
+    GRPO_TRY(make_tmap_blocked(&p1.stash_map_half, w.stash, static_cast<uint64_t>(w.stash_vb),
+                               static_cast<uint64_t>(w.rows_pad / 64), static_cast<uint64_t>(w.stash_vb), 1, 1, 32, 32));
   p1.rows = static_cast<uint32_t>(n);
   p1.vocab = static_cast<uint32_t>(v);
   p1.rows_pad = static_cast<uint32_t>(w.rows_pad);
@@ -480,7 +485,7 @@ static int chunk_backward(const DevInfo& dev, const Workspace& w, const __nv_bfl
     s.m_fast = static_cast<uint32_t>(dev.dh_m_fast);  // 0: all H column blocks of a few row blocks run together
     s.sync_period = static_cast<uint32_t>(dev.sync_dh);
     s.sync_ctr = w.sync + 1;
-    s.probe = dev.clk_probe ? w.probe + 256 : nullptr;
+    s.probe = dev.clk_probe ? w.probe + 1024 : nullptr;
     GRPO_TRY((launch_gemm_any<A_BLOCKED_K, true, EpiBF16<1, kBlockN>, EpiBF16<2, kBlockN>>(
         dev, w.stash, n, w.stash_vb, weight, h, h, v, s, p1, p2, stream)));
   }
@@ -503,7 +508,7 @@ static int chunk_backward(const DevInfo& dev, const Workspace& w, const __nv_bfl
     s.m_fast = 0;  // the H column blocks of one vocab block run together: the stash panel is read from HBM once
     s.sync_period = static_cast<uint32_t>(dev.sync_dw);
     s.sync_ctr = w.sync + 2;
-    s.probe = dev.clk_probe ? w.probe + 512 : nullptr;
+    s.probe = dev.clk_probe ? w.probe + 2048 : nullptr;
     if (dev.l2_hints & 2) {  // the (scaled) hidden chunk is re-read for every vocab block; the stash streams through once
       s.hint_a = kEvictFirst;
       s.hint_b = kEvictLast;
@@ -555,7 +560,7 @@ int grpo_set_option(const char* name, int value) {
   else if (!strcmp(name, "l2_hints")) g_knobs.l2_hints = value;
   else if (!strcmp(name, "dh_m_fast")) g_knobs.dh_m_fast = value;
   else if (!strcmp(name, "wait_hint_ns")) g_knobs.wait_hint_ns = value < 0 ? 0 : value;
-  else if (!strcmp(name, "epi_mode")) g_knobs.epi_mode = value & 3;
+  else if (!strcmp(name, "epi_mode")) g_knobs.epi_mode = value & 7;
   else if (!strcmp(name, "dw_tma")) g_knobs.dw_tma = value != 0;
   else if (!strcmp(name, "st_hint")) g_knobs.st_hint = value & 3;
   else if (!strcmp(name, "clk_probe")) g_knobs.clk_probe = value != 0;

@@ -55,6 +55,7 @@ template <int kCta, int BLOCK_N>
 struct EpiSoftmax {
   struct alignas(64) Params {
     CUtensorMap stash_map;  // store map over the blocked stash, box (64 cols, 32 rows, 1, 1), SWIZZLE_128B; iff mode & 2
+    CUtensorMap stash_map_half;  // the same with box (32 cols, 32 rows, 1, 1), SWIZZLE_64B; iff mode & 4
     uint32_t rows;       // token rows in this launch
     uint32_t vocab;      // V
     uint32_t rows_pad;   // leading dimension of the partial arrays
@@ -67,6 +68,8 @@ struct EpiSoftmax {
     // bit 0: full tiles drain TMEM software-pipelined (the load of column group g+1 is in flight while g is processed)
     // bit 1: (with bit 0) the stash leaves through shared memory and bulk tensor stores, 4 KB per warp and 64 columns,
     //        instead of 16-byte st.global.cs pieces in 32 different 128-byte lines per warp instruction
+    // bit 2: (with bits 0-1) the warp's 4 KB staging buffer is used as two 2 KB halves, one bulk store per 32-column
+    //        group: a half is only rewritten two groups later, so the warp never waits on the store it just issued
     uint32_t mode;
     uint64_t policy;  // L2 eviction priority of the stash stores: it is next read by another kernel, after 5.8 GB went by
   };
@@ -146,6 +149,79 @@ struct EpiSoftmax {
     }
   }
 
+  // exponentials, running sums and bf16 pack of one 32-column group of a full tile (registers only)
+  template <bool kWantEz>
+  __device__ static __forceinline__ void group_pack(const uint32_t (&v)[32], float c1, float off, float& s0, float& s1,
+                                                    float& t0, float& t1, uint32_t (&pk)[16]) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float e[8];
+#pragma unroll
+#if defined(GRPO_EPI_DBG) && (GRPO_EPI_DBG & 1)  // timing experiment only: no MUFU (results are wrong)
+      for (int i = 0; i < 8; ++i) e[i] = fminf(fmaf(__uint_as_float(v[8 * q + i]), c1, -off), kClampLog2);
+#else
+      for (int i = 0; i < 8; ++i) e[i] = fast_exp2(fminf(fmaf(__uint_as_float(v[8 * q + i]), c1, -off), kClampLog2));
+#endif
+#pragma unroll
+      for (int i = 0; i < 8; i += 2) {
+        s0 += e[i];
+        s1 += e[i + 1];
+      }
+      if (kWantEz) {
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) {
+          t0 = fmaf(e[i], __uint_as_float(v[8 * q + i]), t0);
+          t1 = fmaf(e[i + 1], __uint_as_float(v[8 * q + i + 1]), t1);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) pk[4 * q + i] = pack_bf16x2(e[2 * i], e[2 * i + 1]);
+    }
+  }
+
+  // mode bits 0-2: pipelined TMEM drain, one bulk store per 32-column group out of alternating 2 KB staging halves
+  template <bool kWantEz, class Release>
+  __device__ static __forceinline__ void run_half(const Params& p, const EpiCtx& c, uint8_t* smem_epi, Release&& release,
+                                                  float c1, float off, float& s0, float& s1, float& t0, float& t1) {
+    uint8_t* buf = smem_epi + c.epi_warp * kEpiStageBytes;
+    uint8_t* smem_row = buf + c.lane * 64;          // 32 rows x 64 bytes per half
+    const uint32_t sw = (c.lane >> 1) & 3;          // SWIZZLE_64B: 16-byte chunk index ^= bits 7-8 of the address
+    const int32_t rb = static_cast<int32_t>(c.row0 >> 6), r_in = static_cast<int32_t>(c.row0 & 63);
+    const int32_t vb0 = static_cast<int32_t>(c.col0 >> 6);
+    uint32_t va[32], vb[32];
+    auto emit = [&](const uint32_t (&v)[32], int g) {
+      uint32_t pk[16];
+      group_pack<kWantEz>(v, c1, off, s0, s1, t0, t1, pk);
+      uint8_t* half = buf + (g & 1) * 2048;
+#if defined(GRPO_EPI_DBG) && (GRPO_EPI_DBG & 2)  // timing experiment only: nothing leaves the registers
+      if (pk[0] == 0x12345678u && pk[7] == 0x9abcdef0u) s0 += 1.f;
+      return;
+#endif
+      if (c.lane == 0) bulk_wait_read_1();  // the store issued two groups ago (same half) has left shared memory
+      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        st_shared_v4(smem_row + (g & 1) * 2048 + ((q ^ sw) << 4), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (c.lane == 0) {
+        tma_store_4d(&p.stash_map_half, half, (g & 1) * 32, r_in, vb0 + (g >> 1), rb, p.policy);
+        bulk_commit();
+      }
+    };
+    tmem_ld_32x32(c.tmem_acc, va);
+#pragma unroll 1
+    for (int g = 0; g < BLOCK_N / 32; g += 2) {
+      tmem_ld_wait();
+      tmem_ld_32x32(c.tmem_acc + (g + 1) * 32, vb);
+      emit(va, g);
+      tmem_ld_wait();
+      if (g + 2 < BLOCK_N / 32) tmem_ld_32x32(c.tmem_acc + (g + 2) * 32, va);
+      else release();  // last TMEM read of this accumulator has landed
+      emit(vb, g + 1);
+    }
+  }
+
   template <class Release>
   __device__ static void run(const Params& p, const EpiCtx& c, uint8_t* smem_epi, Release&& release) {
     const uint32_t row = c.row, col0 = c.col0;
@@ -166,7 +242,10 @@ struct EpiSoftmax {
     const uint32_t store_groups = want_stash ? min(static_cast<uint32_t>(BLOCK_N / 32), 2 * (p.stash_vb - (col0 >> 6))) : 0;
 
     float s0 = 0.f, s1 = 0.f, t0 = 0.f, t1 = 0.f;
-    if ((p.mode & 1) && ncols == BLOCK_N) {  // every tile but the last one of the vocabulary
+    if ((p.mode & 7) == 7 && want_stash && ncols == BLOCK_N) {
+      if (want_ez) run_half<true>(p, c, smem_epi, release, c1, off, s0, s1, t0, t1);
+      else run_half<false>(p, c, smem_epi, release, c1, off, s0, s1, t0, t1);
+    } else if ((p.mode & 1) && ncols == BLOCK_N) {  // every tile but the last one of the vocabulary
       if (want_ez) run_full<true>(p, c, smem_epi, release, c1, off, srow, s0, s1, t0, t1);
       else run_full<false>(p, c, smem_epi, release, c1, off, srow, s0, s1, t0, t1);
     } else {

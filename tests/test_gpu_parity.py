@@ -117,7 +117,7 @@ def test_epilogue_variants_agree(st, dev):
     (lp_ref * gl).sum().backward()
     outs = {}
     try:
-        for epi, dwt, lead in ((0, 0, 0), (1, 0, 0), (3, 0, 1), (3, 1, 2), (0, 1, 3)):
+        for epi, dwt, lead in ((0, 0, 0), (1, 0, 0), (3, 0, 1), (3, 1, 2), (0, 1, 3), (7, 1, 2)):
             _lib.check(lib.grpo_set_option(b"epi_mode", epi), "set_option")
             _lib.check(lib.grpo_set_option(b"dw_tma", dwt), "set_option")
             _lib.check(lib.grpo_set_option(b"acc_lead", lead), "set_option")
@@ -126,7 +126,7 @@ def test_epilogue_variants_agree(st, dev):
             (lp * gl.to(dev)).sum().backward()
             outs[(epi, dwt, lead)] = (lp.detach().clone(), hd.grad.clone(), wd.grad.clone())
     finally:
-        lib.grpo_set_option(b"epi_mode", 3)
+        lib.grpo_set_option(b"epi_mode", 7)
         lib.grpo_set_option(b"dw_tma", 1)
         lib.grpo_set_option(b"acc_lead", 2)
     base = outs[(0, 0, 0)]

@@ -45,7 +45,7 @@ for spec in args.variants:  # the workspace must fit the largest chunk setting a
     lib.grpo_set_option(b"ksub", 2)
 ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
 DEFAULTS = {"cta_group": 2, "fwd_panel": 4864, "sync_fwd": 28, "sync_dh": 8, "sync_dw": 8, "l2_hints": 0, "dh_m_fast": 0, "chunk_rows": 0, "ksub": 2, "wait_hint_ns": 10000000,
-            "epi_mode": 3, "dw_tma": 1, "acc_lead": 2, "clk_probe": 1, "st_hint": 3}
+            "epi_mode": 7, "dw_tma": 1, "acc_lead": 2, "clk_probe": 1, "st_hint": 3}
 
 
 def apply(spec):
@@ -86,7 +86,7 @@ for rnd in range(args.rounds):
         torch.cuda.synchronize()
         res[spec].append(e0.elapsed_time(e1) / args.iters)
         probe_off = lib.grpo_debug_probe_offset(rows, h, v, 1)  # depends on the variant's chunk size
-        pr = ws[probe_off:probe_off + 3 * 2048].view(torch.int64).cpu().view(3, 256)
+        pr = ws[probe_off:probe_off + 3 * 8192].view(torch.int64).cpu().view(3, 1024)
         for i in range(3):
             c0, n0, c1, n1 = pr[i, :4].tolist()
             if n1 > n0:
