@@ -158,6 +158,52 @@ int grpo_advantage_from_scores(const float* scores_all, const int32_t* order, co
                                grpo_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * The other advantage estimators of the reference's trainer, on the same skeleton.
+ * Masks, `order` / `offsets` and `seq_scratch` (f32 [2*bsz]) as for grpo_advantage; acc_scratch: 4 doubles.
+ *   grpo_rloo_advantage          core_algos.py:179-214  a_i = s_i - (sum_group - s_i) / (n_group - 1), broadcast over mask
+ *   grpo_remax_advantage         core_algos.py:248-273  a_i = s_i - reward_baselines[i], broadcast over mask
+ *   grpo_reinforce_pp_advantage  core_algos.py:217-245  R_t = r_t + gamma * R_{t+1} * mask_{t+1} (returns, out);
+ *                                                      advantages = masked_whiten(R, mask)
+ *   grpo_gae_advantage           core_algos.py:93-133   delta_t = r_t + gamma * v_{t+1} - v_t,
+ *                                                      A_t = delta_t + gamma_lam * A_{t+1}; returns = A + v;
+ *                                                      advantages = masked_whiten(A, mask). gamma_lam = gamma * lambda.
+ * The recurrences run in the reference's fp32 operation order (no FMA contraction): bit-identical to the reference.
+ * ------------------------------------------------------------------------------------------------------------------ */
+int grpo_rloo_advantage(const float* rewards, const void* mask, int mask_dtype, const int32_t* order,
+                        const int32_t* offsets, int64_t bsz, int64_t t_len, int64_t n_groups, float* advantages,
+                        float* seq_scratch, grpo_stream_t stream);
+int grpo_remax_advantage(const float* rewards, const float* reward_baselines, const void* mask, int mask_dtype,
+                         int64_t bsz, int64_t t_len, float* advantages, float* seq_scratch, grpo_stream_t stream);
+int grpo_reinforce_pp_advantage(const float* rewards, const void* mask, int mask_dtype, int64_t bsz, int64_t t_len,
+                                float gamma, float* advantages, float* returns, double* acc_scratch,
+                                grpo_stream_t stream);
+int grpo_gae_advantage(const float* rewards, const float* values, const void* mask, int mask_dtype, int64_t bsz,
+                       int64_t t_len, float gamma, float gamma_lam, float* advantages, float* returns,
+                       double* acc_scratch, grpo_stream_t stream);
+
+/* masked_var / masked_whiten over all elements (torch_functional.py:74-97). acc_scratch: 4 doubles.
+ *   grpo_masked_whiten: out[i] = (values[i] - mean) * rsqrt(var + eps), var unbiased over the mask (out may alias values)
+ *   grpo_masked_var   : out[0] = variance (Bessel-corrected iff unbiased and sum(mask) > 1), out[1] = masked mean */
+int grpo_masked_whiten(const float* values, const void* mask, int mask_dtype, int64_t n, float eps, float* out,
+                       double* acc_scratch, grpo_stream_t stream);
+int grpo_masked_var(const float* values, const void* mask, int mask_dtype, int64_t n, int unbiased, float* out,
+                    double* acc_scratch, grpo_stream_t stream);
+
+/* compute_value_loss (core_algos.py:356-391): out[0] = vf_loss = 0.5 * masked_mean(max((vp - ret)^2, (clip(vp) - ret)^2)),
+ * out[1] = vf_clipfrac; dvpreds f32 [n] (nullable) = d vf_loss / d vpreds. acc_scratch: 4 doubles. */
+int grpo_value_loss_fwd_bwd(const float* vpreds, const float* returns, const float* values, const void* mask,
+                            int mask_dtype, int64_t n, float cliprange_value, float* dvpreds, float* out,
+                            double* acc_scratch, grpo_stream_t stream);
+
+/* apply_kl_penalty (ray_trainer.py:125-145; compute_rewards core_algos.py:276-283 is its kl_mode = GRPO_KL_KL case
+ * without a mask): token_level_rewards = token_level_scores - kl_coef * compute_kl(logp, ref_logp) * mask;
+ * current_kl[0] = mean over sequences of masked_mean(kld, mask, dim=-1). ref_logp == NULL: kld = 0.
+ * All tensors [bsz][t_len]; acc_scratch: 4 doubles. */
+int grpo_kl_penalty_rewards(const float* token_level_scores, const float* logp, const float* ref_logp,
+                            const void* mask, int mask_dtype, int64_t bsz, int64_t t_len, int kl_mode, float kl_coef,
+                            float* token_level_rewards, float* current_kl, double* acc_scratch, grpo_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Ragged micro-batches: run the head on the unmasked response slots only.
  * Replaces: the reference computes log-probs for every slot of the padded [B, T] block and multiplies the padded ones
  * by zero (dp_actor.py:136-139, :253-273); its padding-free branch gathers / scatters tokens for the transformer body

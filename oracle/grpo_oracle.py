@@ -135,6 +135,119 @@ def compute_kl(log_probs: torch.Tensor, ref_log_probs: torch.Tensor, kl_penalty:
 
 
 # ----------------------------------------------------------------------------------------------------------------
+# the rest of core_algos / torch_functional / ray_trainer that shares the elementwise skeleton
+# ----------------------------------------------------------------------------------------------------------------
+def masked_var(values: torch.Tensor, mask: torch.Tensor, unbiased: bool = True) -> torch.Tensor:
+    """verl/utils/torch_functional.py:74-89: masked mean of the squared deviations from the masked mean; Bessel's
+    correction ``M / (M - 1)`` unless ``M = sum(mask) <= 1`` (the reference warns and keeps the biased value)."""
+    dev = values - masked_mean(values, mask)
+    var = masked_mean(dev * dev, mask)
+    if unbiased:
+        m = mask.sum()
+        if m > 1:
+            var = var * (m / (m - 1))
+    return var
+
+
+def masked_whiten(values: torch.Tensor, mask: torch.Tensor, eps: float = 1e-8) -> torch.Tensor:
+    """verl/utils/torch_functional.py:92-95 (every position is transformed, masked or not)."""
+    mu = masked_mean(values, mask)
+    return (values - mu) * torch.rsqrt(masked_var(values, mask) + eps)
+
+
+def _group_rows(index: Sequence) -> Dict[object, List[int]]:
+    members: Dict[object, List[int]] = {}
+    for row, uid in enumerate(index):
+        members.setdefault(uid, []).append(row)
+    return members
+
+
+@torch.no_grad()
+def compute_rloo_outcome_advantage(token_level_rewards: torch.Tensor, response_mask: torch.Tensor, index: Sequence):
+    """verl/trainer/core_algos.py:179-214: score minus the mean of the group's OTHER scores; same object twice."""
+    score = token_level_rewards.sum(dim=-1)
+    out = score.clone()
+    for rows in _group_rows(index).values():
+        assert len(rows) > 1, "RLOO needs rollout.n > 1."
+        total = torch.sum(torch.tensor([score[r] for r in rows]))
+        for r in rows:
+            out[r] = score[r] - (total - score[r]) / (len(rows) - 1)
+    adv = out.unsqueeze(-1) * response_mask
+    return adv, adv
+
+
+@torch.no_grad()
+def compute_remax_outcome_advantage(token_level_rewards: torch.Tensor, reward_baselines: torch.Tensor,
+                                    response_mask: torch.Tensor):
+    """verl/trainer/core_algos.py:248-273."""
+    adv = (token_level_rewards.sum(dim=-1) - reward_baselines).unsqueeze(-1) * response_mask
+    return adv, adv
+
+
+@torch.no_grad()
+def compute_reinforce_plus_plus_outcome_advantage(token_level_rewards: torch.Tensor, response_mask: torch.Tensor,
+                                                  gamma: float):
+    """verl/trainer/core_algos.py:217-245: R_t = r_t + gamma * (R_{t+1} * mask_{t+1}); advantages = whitened R."""
+    t_len = token_level_rewards.shape[1]
+    returns = torch.empty_like(token_level_rewards)
+    tail = torch.zeros_like(token_level_rewards[:, 0])
+    for t in range(t_len - 1, -1, -1):
+        returns[:, t] = token_level_rewards[:, t] + gamma * tail
+        tail = returns[:, t] * response_mask[:, t]
+    return masked_whiten(returns, response_mask), returns
+
+
+@torch.no_grad()
+def compute_gae_advantage_return(token_level_rewards: torch.Tensor, values: torch.Tensor, response_mask: torch.Tensor,
+                                 gamma: float, lam: float):
+    """verl/trainer/core_algos.py:93-133: A_t = (r_t + gamma * v_{t+1} - v_t) + (gamma * lam) * A_{t+1};
+    returns = A + v; advantages = whitened A."""
+    t_len = token_level_rewards.shape[1]
+    adv = torch.empty_like(token_level_rewards)
+    nxt_adv = torch.zeros_like(values[:, 0])
+    nxt_val = torch.zeros_like(values[:, 0])
+    decay = gamma * lam
+    for t in range(t_len - 1, -1, -1):
+        delta = token_level_rewards[:, t] + gamma * nxt_val - values[:, t]
+        nxt_adv = delta + decay * nxt_adv
+        adv[:, t] = nxt_adv
+        nxt_val = values[:, t]
+    return masked_whiten(adv, response_mask), adv + values
+
+
+def compute_rewards(token_level_scores: torch.Tensor, log_probs: torch.Tensor, ref_log_probs: torch.Tensor,
+                    kl_ratio: float) -> torch.Tensor:
+    """verl/trainer/core_algos.py:276-283."""
+    return token_level_scores - (log_probs - ref_log_probs) * kl_ratio
+
+
+def compute_value_loss(vpreds: torch.Tensor, returns: torch.Tensor, values: torch.Tensor, action_mask: torch.Tensor,
+                       cliprange_value: float):
+    """verl/trainer/core_algos.py:356-391: (vf_loss, vf_clipfrac)."""
+    clipped = torch.min(torch.max(vpreds, values - cliprange_value), values + cliprange_value)
+    err_plain = (vpreds - returns) ** 2
+    err_clip = (clipped - returns) ** 2
+    loss = 0.5 * masked_mean(torch.max(err_plain, err_clip), action_mask)
+    frac = masked_mean((err_plain < err_clip).float(), action_mask)
+    return loss, frac
+
+
+@torch.no_grad()
+def kl_penalty_rewards(token_level_scores: torch.Tensor, old_log_probs: Optional[torch.Tensor],
+                       ref_log_probs: Optional[torch.Tensor], response_mask: torch.Tensor, kl_coef: float,
+                       kl_penalty: str = "kl"):
+    """The arithmetic of apply_kl_penalty, verl/trainer/ray_trainer.py:125-145:
+    (token_level_rewards, current_kl) with current_kl the batch mean of the per-sequence masked means of kld."""
+    if ref_log_probs is not None:
+        kld = compute_kl(old_log_probs, ref_log_probs, kl_penalty) * response_mask
+    else:
+        kld = torch.zeros_like(response_mask, dtype=torch.float32)
+    rewards = token_level_scores - kl_coef * kld
+    per_seq = masked_mean(kld, response_mask, dim=-1)
+    return rewards, float(per_seq.mean(dim=0))
+
+
+# ----------------------------------------------------------------------------------------------------------------
 # lm_head + micro-batch arithmetic (dp_actor.py)
 # ----------------------------------------------------------------------------------------------------------------
 def lm_head_log_probs(

@@ -53,6 +53,14 @@ _SIGNATURES = {
     "grpo_advantage": (c_int, [_P, _P, c_int, _P, _P, c_int64, c_int64, c_int64, c_float, _P, _P, _P]),
     "grpo_sequence_scores": (c_int, [_P, c_int64, c_int64, _P, _P]),
     "grpo_advantage_from_scores": (c_int, [_P, _P, _P, c_int64, c_int64, c_float, c_int64, _P, c_int, c_int64, c_int64, _P, _P, _P]),
+    "grpo_rloo_advantage": (c_int, [_P, _P, c_int, _P, _P, c_int64, c_int64, c_int64, _P, _P, _P]),
+    "grpo_remax_advantage": (c_int, [_P, _P, _P, c_int, c_int64, c_int64, _P, _P, _P]),
+    "grpo_reinforce_pp_advantage": (c_int, [_P, _P, c_int, c_int64, c_int64, c_float, _P, _P, _P, _P]),
+    "grpo_gae_advantage": (c_int, [_P, _P, _P, c_int, c_int64, c_int64, c_float, c_float, _P, _P, _P, _P]),
+    "grpo_masked_whiten": (c_int, [_P, _P, c_int, c_int64, c_float, _P, _P, _P]),
+    "grpo_masked_var": (c_int, [_P, _P, c_int, c_int64, c_int, _P, _P, _P]),
+    "grpo_value_loss_fwd_bwd": (c_int, [_P, _P, _P, _P, c_int, c_int64, c_float, _P, _P, _P, _P]),
+    "grpo_kl_penalty_rewards": (c_int, [_P, _P, _P, _P, c_int, c_int64, c_int64, c_int, c_float, _P, _P, _P, _P]),
     "grpo_compact_scratch_bytes": (c_size_t, [c_int64]),
     "grpo_compact_index": (c_int, [_P, c_int, c_int64, _P, _P, _P, _P, c_size_t, _P]),
     "grpo_gather_rows": (c_int, [_P, _P, c_int64, c_int64, _P, _P]),

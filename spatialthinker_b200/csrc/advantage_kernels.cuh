@@ -10,25 +10,27 @@
 
 namespace grpo {
 
-// one warp per sequence: scores[i] = sum_t rewards[i][t]
+// one warp per sequence: scores[i] = sum_t rewards[i][t]. Accumulated in fp64 and rounded once: with one reward per
+// sequence (the reference's reward functions) that is the reference's fp32 sum exactly, with per-token rewards (after
+// KL shaping) it is the correctly rounded sum, whatever order torch's own fp32 reduction happens to use.
 __global__ void row_score_kernel(const float* __restrict__ rewards, uint32_t bsz, uint32_t t_len,
                                  float* __restrict__ scores) {
   const uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t lane = threadIdx.x & 31;
   if (row >= bsz) return;
   const float* r = rewards + static_cast<size_t>(row) * t_len;
-  float s = 0.f;
+  double s = 0.0;
   if ((t_len & 3u) == 0 && (reinterpret_cast<uintptr_t>(r) & 15u) == 0) {
     const float4* r4 = reinterpret_cast<const float4*>(r);
     for (uint32_t i = lane; i < (t_len >> 2); i += 32) {
       const float4 q = r4[i];
-      s += (q.x + q.y) + (q.z + q.w);
+      s += (static_cast<double>(q.x) + static_cast<double>(q.y)) + (static_cast<double>(q.z) + static_cast<double>(q.w));
     }
   } else {
-    for (uint32_t i = lane; i < t_len; i += 32) s += r[i];
+    for (uint32_t i = lane; i < t_len; i += 32) s += static_cast<double>(r[i]);
   }
   s = warp_sum(s);
-  if (lane == 0) scores[row] = s;
+  if (lane == 0) scores[row] = static_cast<float>(s);
 }
 
 // one warp per group: warp-shuffle mean / unbiased std in fp64, then the per-sequence normalised score

@@ -13,6 +13,7 @@
 
 #include "advantage_kernels.cuh"
 #include "compact_kernels.cuh"
+#include "estimator_kernels.cuh"
 #include "gemm_core.cuh"
 #include "lmhead_kernels.cuh"
 #include "logits_kernels.cuh"
@@ -767,10 +768,11 @@ int grpo_masked_mean(const float* x, const void* mask, int mask_dtype, int64_t n
     return fail(GRPO_ERR_ARG, "bad mask / mask_dtype");
   if (n < 0) return fail(GRPO_ERR_ARG, "negative length");
   GRPO_CUDA(cudaMemsetAsync(acc_scratch, 0, 2 * sizeof(double), stream));
-  if (n > 0)
+  if (n > 0) {
     masked_sum_kernel<<<ew_blocks(n, 256, 0), 256, 0, stream>>>(x, mask, mask_dtype, static_cast<size_t>(n),
                                                                 acc_scratch);
     count_launch();
+  }
   masked_mean_finalize_kernel<<<1, 32, 0, stream>>>(acc_scratch, eps, out);
   count_launch();
   GRPO_CUDA(cudaGetLastError());
@@ -833,6 +835,170 @@ int grpo_advantage(const float* rewards, const void* mask, int mask_dtype, const
   count_launch();
   broadcast_adv_kernel<<<ew_blocks(bsz * t_len, 256, 0), 256, 0, stream>>>(seq_adv, mask, mask_dtype, b, t,
                                                                            advantages);
+  count_launch();
+  GRPO_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ other estimators
+static int check_seq_args(const void* mask, int mask_dtype, int64_t bsz, int64_t t_len) {
+  if (mask_dtype < 0 || mask_dtype > 3 || (mask_dtype != MASK_NONE && !mask))
+    return fail(GRPO_ERR_ARG, "bad mask / mask_dtype");
+  if (bsz < 0 || t_len < 0 || bsz > 0x7fffffffll || t_len > 0x7fffffffll) return fail(GRPO_ERR_ARG, "bad dimensions");
+  return 0;
+}
+
+int grpo_rloo_advantage(const float* rewards, const void* mask, int mask_dtype, const int32_t* order,
+                        const int32_t* offsets, int64_t bsz, int64_t t_len, int64_t n_groups, float* advantages,
+                        float* seq_scratch, grpo_stream_t stream) {
+  if (!rewards || !order || !offsets || !advantages || !seq_scratch)
+    return fail(GRPO_ERR_ARG, "rewards / order / offsets / advantages / seq_scratch must not be null");
+  GRPO_TRY(check_seq_args(mask, mask_dtype, bsz, t_len));
+  if (n_groups < 0) return fail(GRPO_ERR_ARG, "bad dimensions");
+  if (bsz == 0 || t_len == 0) return 0;
+  float* scores = seq_scratch;
+  float* seq_adv = seq_scratch + bsz;
+  const uint32_t b = static_cast<uint32_t>(bsz), t = static_cast<uint32_t>(t_len);
+  row_score_kernel<<<cdiv(bsz * 32, 256), 256, 0, stream>>>(rewards, b, t, scores);
+  group_rloo_kernel<<<cdiv(n_groups * 32, 256), 256, 0, stream>>>(scores, order, offsets,
+                                                                  static_cast<uint32_t>(n_groups), seq_adv);
+  broadcast_adv_kernel<<<ew_blocks(bsz * t_len, 256, 0), 256, 0, stream>>>(seq_adv, mask, mask_dtype, b, t,
+                                                                           advantages);
+  count_launch(3);
+  GRPO_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int grpo_remax_advantage(const float* rewards, const float* reward_baselines, const void* mask, int mask_dtype,
+                         int64_t bsz, int64_t t_len, float* advantages, float* seq_scratch, grpo_stream_t stream) {
+  if (!rewards || !reward_baselines || !advantages || !seq_scratch)
+    return fail(GRPO_ERR_ARG, "rewards / reward_baselines / advantages / seq_scratch must not be null");
+  GRPO_TRY(check_seq_args(mask, mask_dtype, bsz, t_len));
+  if (bsz == 0 || t_len == 0) return 0;
+  float* scores = seq_scratch;
+  float* seq_adv = seq_scratch + bsz;
+  const uint32_t b = static_cast<uint32_t>(bsz), t = static_cast<uint32_t>(t_len);
+  row_score_kernel<<<cdiv(bsz * 32, 256), 256, 0, stream>>>(rewards, b, t, scores);
+  remax_seq_kernel<<<cdiv(bsz, 256), 256, 0, stream>>>(scores, reward_baselines, b, seq_adv);
+  broadcast_adv_kernel<<<ew_blocks(bsz * t_len, 256, 0), 256, 0, stream>>>(seq_adv, mask, mask_dtype, b, t,
+                                                                           advantages);
+  count_launch(3);
+  GRPO_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// whiten `x` over the mask into `out` (may alias x); acc_scratch: 3 doubles
+static int whiten_launch(const float* x, const void* mask, int mask_dtype, int64_t n, float eps, float* out,
+                         double* acc, cudaStream_t stream) {
+  GRPO_CUDA(cudaMemsetAsync(acc, 0, 3 * sizeof(double), stream));
+  const uint32_t blocks = ew_blocks(n, 256, 0);
+  const size_t sn = static_cast<size_t>(n);
+  masked_sum_kernel<<<blocks, 256, 0, stream>>>(x, mask, mask_dtype, sn, acc);
+  masked_centered_sq_kernel<<<blocks, 256, 0, stream>>>(x, mask, mask_dtype, sn, acc);
+  if (out != nullptr) {
+    whiten_apply_kernel<<<blocks, 256, 0, stream>>>(x, sn, acc, eps, out);
+    count_launch();
+  }
+  count_launch(2);
+  return 0;
+}
+
+int grpo_masked_whiten(const float* values, const void* mask, int mask_dtype, int64_t n, float eps, float* out,
+                       double* acc_scratch, grpo_stream_t stream) {
+  if (!values || !out || !acc_scratch) return fail(GRPO_ERR_ARG, "values / out / acc_scratch must not be null");
+  GRPO_TRY(check_seq_args(mask, mask_dtype, n, 1));
+  if (n == 0) return 0;
+  GRPO_TRY(whiten_launch(values, mask, mask_dtype, n, eps, out, acc_scratch, stream));
+  GRPO_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int grpo_masked_var(const float* values, const void* mask, int mask_dtype, int64_t n, int unbiased, float* out,
+                    double* acc_scratch, grpo_stream_t stream) {
+  if (!values || !out || !acc_scratch) return fail(GRPO_ERR_ARG, "values / out / acc_scratch must not be null");
+  GRPO_TRY(check_seq_args(mask, mask_dtype, n, 1));
+  if (n == 0) {
+    GRPO_CUDA(cudaMemsetAsync(acc_scratch, 0, 3 * sizeof(double), stream));
+  } else {
+    GRPO_TRY(whiten_launch(values, mask, mask_dtype, n, 0.f, nullptr, acc_scratch, stream));
+  }
+  masked_var_finalize_kernel<<<1, 32, 0, stream>>>(acc_scratch, unbiased, out);
+  count_launch();
+  GRPO_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int grpo_reinforce_pp_advantage(const float* rewards, const void* mask, int mask_dtype, int64_t bsz, int64_t t_len,
+                                float gamma, float* advantages, float* returns, double* acc_scratch,
+                                grpo_stream_t stream) {
+  if (!rewards || !advantages || !returns || !acc_scratch)
+    return fail(GRPO_ERR_ARG, "rewards / advantages / returns / acc_scratch must not be null");
+  GRPO_TRY(check_seq_args(mask, mask_dtype, bsz, t_len));
+  if (bsz == 0 || t_len == 0) return 0;
+  reverse_scan_kernel<<<cdiv(bsz, kScanTile * kScanWarps), kScanWarps * 32, 0, stream>>>(
+      1, rewards, nullptr, mask, mask_dtype, static_cast<uint32_t>(bsz), static_cast<uint32_t>(t_len), gamma, 0.f,
+      nullptr, returns);
+  count_launch();
+  GRPO_TRY(whiten_launch(returns, mask, mask_dtype, bsz * t_len, 1e-8f, advantages, acc_scratch, stream));
+  GRPO_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int grpo_gae_advantage(const float* rewards, const float* values, const void* mask, int mask_dtype, int64_t bsz,
+                       int64_t t_len, float gamma, float gamma_lam, float* advantages, float* returns,
+                       double* acc_scratch, grpo_stream_t stream) {
+  if (!rewards || !values || !advantages || !returns || !acc_scratch)
+    return fail(GRPO_ERR_ARG, "rewards / values / advantages / returns / acc_scratch must not be null");
+  GRPO_TRY(check_seq_args(mask, mask_dtype, bsz, t_len));
+  if (bsz == 0 || t_len == 0) return 0;
+  reverse_scan_kernel<<<cdiv(bsz, kScanTile * kScanWarps), kScanWarps * 32, 0, stream>>>(
+      0, rewards, values, nullptr, MASK_NONE, static_cast<uint32_t>(bsz), static_cast<uint32_t>(t_len), gamma,
+      gamma_lam, advantages, returns);
+  count_launch();
+  GRPO_TRY(whiten_launch(advantages, mask, mask_dtype, bsz * t_len, 1e-8f, advantages, acc_scratch, stream));
+  GRPO_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int grpo_value_loss_fwd_bwd(const float* vpreds, const float* returns, const float* values, const void* mask,
+                            int mask_dtype, int64_t n, float cliprange_value, float* dvpreds, float* out,
+                            double* acc_scratch, grpo_stream_t stream) {
+  if (!vpreds || !returns || !values || !out || !acc_scratch)
+    return fail(GRPO_ERR_ARG, "vpreds / returns / values / out / acc_scratch must not be null");
+  GRPO_TRY(check_seq_args(mask, mask_dtype, n, 1));
+  GRPO_CUDA(cudaMemsetAsync(acc_scratch, 0, 3 * sizeof(double), stream));
+  if (n > 0) {
+    const uint32_t blocks = ew_blocks(n, 256, 0);
+    mask_sum_kernel<<<blocks, 256, 0, stream>>>(mask, mask_dtype, static_cast<size_t>(n), acc_scratch);
+    value_loss_kernel<<<blocks, 256, 0, stream>>>(vpreds, returns, values, mask, mask_dtype, static_cast<size_t>(n),
+                                                  cliprange_value, acc_scratch, dvpreds);
+    count_launch(2);
+  }
+  value_loss_finalize_kernel<<<1, 32, 0, stream>>>(acc_scratch, out);
+  count_launch();
+  GRPO_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int grpo_kl_penalty_rewards(const float* token_level_scores, const float* logp, const float* ref_logp,
+                            const void* mask, int mask_dtype, int64_t bsz, int64_t t_len, int kl_mode, float kl_coef,
+                            float* token_level_rewards, float* current_kl, double* acc_scratch,
+                            grpo_stream_t stream) {
+  if (!token_level_scores || !token_level_rewards || !current_kl || !acc_scratch)
+    return fail(GRPO_ERR_ARG, "token_level_scores / token_level_rewards / current_kl / acc_scratch must not be null");
+  if (ref_logp && !logp) return fail(GRPO_ERR_ARG, "ref_logp given without logp");
+  if (ref_logp && (kl_mode < GRPO_KL_LOW_VAR || kl_mode > GRPO_KL_CHI2))
+    return fail(GRPO_ERR_ARG, "unknown kl_mode %d", kl_mode);
+  GRPO_TRY(check_seq_args(mask, mask_dtype, bsz, t_len));
+  if (bsz == 0) return 0;
+  GRPO_CUDA(cudaMemsetAsync(acc_scratch, 0, sizeof(double), stream));
+  if (t_len > 0) {
+    kl_reward_kernel<<<cdiv(bsz * 32, 256), 256, 0, stream>>>(token_level_scores, logp, ref_logp, mask, mask_dtype,
+                                                              static_cast<uint32_t>(bsz), static_cast<uint32_t>(t_len),
+                                                              kl_mode, kl_coef, token_level_rewards, acc_scratch);
+    count_launch();
+  }
+  kl_reward_finalize_kernel<<<1, 32, 0, stream>>>(acc_scratch, static_cast<uint32_t>(bsz), current_kl);
   count_launch();
   GRPO_CUDA(cudaGetLastError());
   return 0;

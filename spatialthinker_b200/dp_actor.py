@@ -89,9 +89,9 @@ class DataParallelPPOActor:
 
     # ------------------------------------------------------------------------------------------------------------
     def _hidden(self, micro: Dict[str, Any], train: bool) -> torch.Tensor:
-        if "hidden_states" in micro:
-            return micro["hidden_states"]
-        if self.hidden_fn is None:
+        if self.hidden_fn is None:  # an actor built with hidden_fn always runs it (e.g. a reference policy whose
+            if "hidden_states" in micro:  # hidden states travel under another key of the same batch)
+                return micro["hidden_states"]
             raise KeyError("batch has no 'hidden_states' and the actor was built without hidden_fn")
         if train:
             return self.hidden_fn(micro)

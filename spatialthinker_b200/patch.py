@@ -49,9 +49,13 @@ def patch_verl(*, advantages: bool = True, loss: bool = True, log_probs: bool = 
     if log_probs:
         plan += [(vf, "log_probs_from_logits", my_vf.log_probs_from_logits), (vf, "masked_mean", my_vf.masked_mean)]
     if advantages:
-        plan += [(ca, "compute_grpo_outcome_advantage", my_ca.compute_grpo_outcome_advantage)]
+        plan += [(ca, name, getattr(my_ca, name)) for name in (
+            "compute_grpo_outcome_advantage", "compute_rloo_outcome_advantage", "compute_remax_outcome_advantage",
+            "compute_reinforce_plus_plus_outcome_advantage", "compute_gae_advantage_return")]
+        plan += [(vf, "masked_whiten", my_vf.masked_whiten)]
     if loss:
-        plan += [(ca, "compute_policy_loss", my_ca.compute_policy_loss), (ca, "compute_kl", my_ca.compute_kl)]
+        plan += [(ca, "compute_policy_loss", my_ca.compute_policy_loss), (ca, "compute_kl", my_ca.compute_kl),
+                 (ca, "compute_value_loss", my_ca.compute_value_loss)]
     for mod, name, fn in plan:
         key = (mod.__name__, name)
         if key not in _SAVED:

@@ -1,4 +1,4 @@
-"""Drop-in for the hot-path part of ``verl/utils/torch_functional.py`` (lines 26-71 of the reference).
+"""Drop-in for the hot-path part of ``verl/utils/torch_functional.py`` (lines 26-97 of the reference).
 
 Same names, argument meaning and return conventions as the reference; the arithmetic runs in hand-written CUDA
 (``csrc/logits_kernels.cuh``, ``csrc/loss_kernels.cuh``) through the C ABI. The upstream-veRL spellings named by the
@@ -130,3 +130,39 @@ def masked_mean(values: torch.Tensor, mask: torch.Tensor, dim: Optional[int] = N
         return _MaskedMeanAll.apply(values, mask, eps)
     require_cuda(values, mask)
     return (values * mask).sum(dim=dim) / (mask.sum(dim=dim) + eps)
+
+
+def _masked_moments(values: torch.Tensor, mask: torch.Tensor, unbiased: bool) -> torch.Tensor:
+    dev = require_cuda(values, mask)
+    lib = _lib.load()
+    x = f32c(values).view(-1)
+    m, code = mask_arg(mask.expand_as(values) if mask.shape != values.shape else mask)
+    out = torch.empty(2, dtype=torch.float32, device=dev)
+    acc = torch.empty(4, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.grpo_masked_var(x.data_ptr(), m.data_ptr(), code, x.numel(), int(bool(unbiased)), out.data_ptr(),
+                                       acc.data_ptr(), _lib.stream_ptr(dev)), "grpo_masked_var")
+    return out
+
+
+@torch.no_grad()
+def masked_var(values: torch.Tensor, mask: torch.Tensor, unbiased: bool = True) -> torch.Tensor:
+    """Variance over the masked entries - verl/utils/torch_functional.py:74-89 (Bessel's correction unless
+    ``sum(mask) <= 1``, where the reference prints a warning and returns the biased value). Not differentiable here:
+    the reference only uses it under ``torch.no_grad`` (advantage whitening)."""
+    return _masked_moments(values, mask, unbiased)[0]
+
+
+@torch.no_grad()
+def masked_whiten(values: torch.Tensor, mask: torch.Tensor, eps: float = 1e-8) -> torch.Tensor:
+    """``(values - masked_mean) * rsqrt(masked_var + eps)`` at every position - torch_functional.py:92-95."""
+    dev = require_cuda(values, mask)
+    lib = _lib.load()
+    x = f32c(values)
+    m, code = mask_arg(mask.expand_as(values) if mask.shape != values.shape else mask)
+    out = torch.empty_like(x)
+    acc = torch.empty(4, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.grpo_masked_whiten(x.data_ptr(), m.data_ptr(), code, x.numel(), float(eps), out.data_ptr(),
+                                          acc.data_ptr(), _lib.stream_ptr(dev)), "grpo_masked_whiten")
+    return out

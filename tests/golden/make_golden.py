@@ -152,12 +152,81 @@ def kat_end_to_end():
     np.savez_compressed(os.path.join(OUT, "end_to_end.npz"), **out)
 
 
+def kat_estimators():
+    """RLOO / ReMax / REINFORCE++ / GAE, masked_var / masked_whiten, value loss, KL reward shaping
+    - outputs of the reference's own functions; apply_kl_penalty's arithmetic (ray_trainer.py:131-142) is typed out with
+    the reference's compute_kl / masked_mean because ray_trainer.py itself imports ray."""
+    out = {}
+    g = torch.Generator().manual_seed(33)
+    for tag, bsz, n, t in (("s", 12, 4, 7), ("m", 64, 8, 45), ("l", 48, 16, 100)):
+        lens = torch.randint(1, t + 1, (bsz,), generator=g)
+        lens[0] = t
+        mask = (torch.arange(t)[None] < lens[:, None]).long()
+        sparse = torch.zeros(bsz, t)
+        sparse[torch.arange(bsz), lens - 1] = torch.rand(bsz, generator=g)
+        dense = torch.randn(bsz, t, generator=g) * mask  # per-token rewards (after KL shaping every token carries one)
+        values = torch.randn(bsz, t, generator=g)
+        baselines = torch.rand(bsz, generator=g)
+        uid = np.repeat(np.array([f"u{i}" for i in range(bsz // n)], dtype=object), n)[torch.randperm(bsz, generator=g).numpy()]
+        out.update({f"{tag}_mask": mask.numpy(), f"{tag}_sparse": sparse.numpy(), f"{tag}_dense": dense.numpy(),
+                    f"{tag}_values": values.numpy(), f"{tag}_baselines": baselines.numpy(), f"{tag}_uid": uid.astype(str)})
+        for rname, rew in (("sparse", sparse), ("dense", dense)):
+            a, r = ca.compute_rloo_outcome_advantage(rew.clone(), mask, uid)
+            assert a is r
+            out[f"{tag}_{rname}_rloo"] = a.numpy()
+            a, r = ca.compute_remax_outcome_advantage(rew.clone(), baselines, mask)
+            assert a is r
+            out[f"{tag}_{rname}_remax"] = a.numpy()
+            for gamma in (1.0, 0.97):
+                a, r = ca.compute_reinforce_plus_plus_outcome_advantage(rew.clone(), mask, gamma)
+                out[f"{tag}_{rname}_rpp_adv_{gamma}"] = a.numpy()
+                out[f"{tag}_{rname}_rpp_ret_{gamma}"] = r.numpy()
+            for gamma, lam in ((1.0, 1.0), (0.99, 0.95)):
+                a, r = ca.compute_gae_advantage_return(rew.clone(), values, mask, gamma, lam)
+                out[f"{tag}_{rname}_gae_adv_{gamma}_{lam}"] = a.numpy()
+                out[f"{tag}_{rname}_gae_ret_{gamma}_{lam}"] = r.numpy()
+        out[f"{tag}_var"] = np.array([float(VF.masked_var(values, mask)), float(VF.masked_var(values, mask, unbiased=False))],
+                                     dtype=np.float32)
+        out[f"{tag}_whiten"] = VF.masked_whiten(values, mask).numpy()
+        # value loss with gradient
+        vp = (values + 0.4 * torch.randn(bsz, t, generator=g)).requires_grad_(True)
+        ret = values + 0.5 * torch.randn(bsz, t, generator=g)
+        loss, frac = ca.compute_value_loss(vp, ret, values, mask, 0.5)
+        loss.backward()
+        out.update({f"{tag}_vpreds": vp.detach().numpy(), f"{tag}_returns": ret.numpy(),
+                    f"{tag}_vf": np.array([float(loss), float(frac)], dtype=np.float32), f"{tag}_vf_grad": vp.grad.numpy()})
+        # KL reward shaping, every estimator
+        old = -2.0 * torch.rand(bsz, t, generator=g)
+        ref = old + 0.3 * torch.randn(bsz, t, generator=g)
+        ref[1, :2] -= 6.0
+        out.update({f"{tag}_old": old.numpy(), f"{tag}_ref": ref.numpy()})
+        for mode in ("kl", "abs", "mse", "low_var_kl", "chi2"):
+            kld = ca.compute_kl(old, ref, kl_penalty=mode) * mask
+            rewards = sparse - 0.05 * kld
+            cur = torch.mean(VF.masked_mean(kld, mask=mask, dim=-1), dim=0).item()
+            out[f"{tag}_klrew_{mode}"] = rewards.numpy()
+            out[f"{tag}_klcur_{mode}"] = np.array([cur], dtype=np.float32)
+        out[f"{tag}_compute_rewards"] = ca.compute_rewards(sparse, old, ref, 0.05).numpy()
+    # degenerate masks for masked_var: one valid element -> biased value returned, none -> 0
+    x = torch.tensor([[1.0, 2.0, 4.0]])
+    out["var_one"] = np.array([float(VF.masked_var(x, torch.tensor([[0, 1, 0]])))], dtype=np.float32)
+    # KL controllers
+    ctl = ca.AdaptiveKLController(init_kl_coef=0.01, target_kl=0.1, horizon=1000.0)
+    trace = []
+    for cur in (0.05, 0.2, 0.11, 0.0):
+        ctl.update(current_kl=cur, n_steps=128)
+        trace.append(ctl.kl_coef)
+    out["adaptive_kl_trace"] = np.array(trace, dtype=np.float64)
+    np.savez_compressed(os.path.join(OUT, "estimators.npz"), **out)
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     torch.set_num_threads(4)
-    kat_advantage()
-    kat_policy_loss()
-    kat_end_to_end()
+    todo = sys.argv[1:] or ["advantage", "policy_loss", "end_to_end", "estimators"]
+    for name in todo:
+        {"advantage": kat_advantage, "policy_loss": kat_policy_loss, "end_to_end": kat_end_to_end,
+         "estimators": kat_estimators}[name]()
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)), "bytes")
