@@ -61,14 +61,22 @@ __global__ void group_stats_kernel(const float* __restrict__ scores, const int32
   }
 }
 
-// advantages[i][t] = seq_adv[i] * mask[i][t]
+// advantages[i][t] = seq_adv[i] * mask[i][t]     grid (column blocks, row blocks): no per-element index division
 __global__ void broadcast_adv_kernel(const float* __restrict__ seq_adv, const void* __restrict__ mask, int mask_dtype,
                                      uint32_t bsz, uint32_t t_len, float* __restrict__ adv) {
-  const size_t n = static_cast<size_t>(bsz) * t_len;
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const uint32_t row = static_cast<uint32_t>(i / t_len);
-    adv[i] = seq_adv[row] * load_mask(mask, mask_dtype, i);
+  const uint32_t t_step = gridDim.x * blockDim.x;
+  for (uint32_t row = blockIdx.y; row < bsz; row += gridDim.y) {
+    const float a = seq_adv[row];
+    const size_t base = static_cast<size_t>(row) * t_len;
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    for (; t + 3 * t_step < t_len; t += 4 * t_step) {
+      float m[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) m[u] = load_mask(mask, mask_dtype, base + t + u * t_step);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) adv[base + t + u * t_step] = a * m[u];
+    }
+    for (; t < t_len; t += t_step) adv[base + t] = a * load_mask(mask, mask_dtype, base + t);
   }
 }
 

@@ -47,60 +47,92 @@ __global__ void remax_seq_kernel(const float* __restrict__ scores, const float* 
 // The reference walks the response from its last token to its first with one fp32 recurrence per sequence. Here a
 // warp owns 32 sequences: 32 x 32 tiles travel through shared memory so that global accesses are coalesced along the
 // token axis while lane r runs sequence r's recurrence in the reference's own operation order (no FMA contraction:
-// the results are the reference's bit for bit).
+// the results are the reference's bit for bit). The kernel is latency-bound, not bandwidth-bound (one dependency chain
+// of T steps per sequence, 32 sequences per SM-resident warp), so the loads of the NEXT tile are issued into registers
+// before the current tile's recurrence runs, all 64 of them independent.
 constexpr int kScanTile = 32;
-constexpr int kScanWarps = 4;
 
 // mode 0 - GAE (core_algos.py:122-130):   delta_t = (r_t + gamma * v_{t+1}) - v_t;   A_t = delta_t + (gamma*lam) * A_{t+1}
 //                                         out_a = A (before whitening), out_b = A + v (returns)
 // mode 1 - REINFORCE++ (:236-242):        R_t = r_t + gamma * (R_{t+1} * mask_{t+1});   out_b = R (returns)
-__global__ void __launch_bounds__(kScanWarps * 32)
-reverse_scan_kernel(int mode, const float* __restrict__ rewards, const float* __restrict__ values,
-                    const void* __restrict__ mask, int mask_dtype, uint32_t bsz, uint32_t t_len, float gamma,
-                    float gamma_lam, float* __restrict__ out_a, float* __restrict__ out_b) {
-  __shared__ float tile_x[kScanWarps][kScanTile][kScanTile + 1];
-  __shared__ float tile_y[kScanWarps][kScanTile][kScanTile + 1];
-  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t row0 = (blockIdx.x * kScanWarps + warp) * kScanTile;
+// MaskT / kHasMask: element type and presence of the mask (mode 1; no mask = all ones). Compile-time, not load_mask's
+// run-time switch: a branch per element between the 64 loads of a tile serialises them, each waiting out a DRAM round
+// trip (measured: 4x slower).
+template <int kMode, typename MaskT, bool kHasMask>
+__global__ void __launch_bounds__(32)
+reverse_scan_kernel(const float* __restrict__ rewards, const float* __restrict__ values, const MaskT* __restrict__ mask,
+                    uint32_t bsz, uint32_t t_len, float gamma, float gamma_lam, float* __restrict__ out_a,
+                    float* __restrict__ out_b) {
+  __shared__ float x[kScanTile][kScanTile + 1];
+  __shared__ float y[kScanTile][kScanTile + 1];
+  const uint32_t lane = threadIdx.x;
+  const uint32_t row0 = blockIdx.x * kScanTile;
   if (row0 >= bsz) return;
-  float(*x)[kScanTile + 1] = tile_x[warp];
-  float(*y)[kScanTile + 1] = tile_y[warp];
   const uint32_t nrows = min(static_cast<uint32_t>(kScanTile), bsz - row0);
+  const uint32_t tiles = (t_len + kScanTile - 1) / kScanTile;
+  float rx[kScanTile], ry[kScanTile];
+  auto fetch = [&](uint32_t tb) {
+    const uint32_t t = tb * kScanTile + lane;
+    const bool col_ok = t < t_len;
+#pragma unroll
+    for (int r = 0; r < kScanTile; ++r) {
+      const bool ok = col_ok && static_cast<uint32_t>(r) < nrows;
+      const size_t idx = static_cast<size_t>(row0 + r) * t_len + t;
+      rx[r] = ok ? rewards[idx] : 0.f;
+      if (kMode == 0) ry[r] = ok ? values[idx] : 0.f;
+      else if (kHasMask) ry[r] = ok ? static_cast<float>(mask[idx]) : 0.f;
+      else ry[r] = ok ? 1.f : 0.f;
+    }
+  };
   float carry = 0.f;       // A_{t+1} or R_{t+1} * mask_{t+1}
   float next_value = 0.f;  // v_{t+1} (GAE)
-  const uint32_t tiles = (t_len + kScanTile - 1) / kScanTile;
+  fetch(tiles - 1);
   for (uint32_t tb = tiles; tb-- > 0;) {
     const uint32_t t0 = tb * kScanTile;
-    const uint32_t t = t0 + lane;
-    for (uint32_t r = 0; r < nrows; ++r) {
-      const size_t idx = static_cast<size_t>(row0 + r) * t_len + t;
-      const bool ok = t < t_len;
-      x[r][lane] = ok ? rewards[idx] : 0.f;
-      y[r][lane] = !ok ? 0.f : (mode == 0 ? values[idx] : load_mask(mask, mask_dtype, idx));
+#pragma unroll
+    for (int r = 0; r < kScanTile; ++r) {
+      x[r][lane] = rx[r];
+      y[r][lane] = ry[r];
     }
     __syncwarp();
+    if (tb > 0) fetch(tb - 1);  // in flight while the recurrence below runs
     if (lane < nrows) {
-      const uint32_t steps = min(static_cast<uint32_t>(kScanTile), t_len - t0);
-      for (uint32_t j = steps; j-- > 0;) {
-        if (mode == 0) {
-          const float v = y[lane][j];
-          const float delta = __fsub_rn(__fadd_rn(x[lane][j], __fmul_rn(gamma, next_value)), v);
+      // this lane's 32 tokens go to registers first (64 independent shared loads), so that the dependency chain below
+      // is arithmetic only. Slots past t_len hold zeros and leave the carried state at +0, exactly as if skipped.
+      float xs[kScanTile], ys[kScanTile];
+#pragma unroll
+      for (int j = 0; j < kScanTile; ++j) {
+        xs[j] = x[lane][j];
+        ys[j] = y[lane][j];
+      }
+#pragma unroll
+      for (int j = kScanTile - 1; j >= 0; --j) {
+        if (kMode == 0) {
+          const float v = ys[j];
+          const float delta = __fsub_rn(__fadd_rn(xs[j], __fmul_rn(gamma, next_value)), v);
           carry = __fadd_rn(delta, __fmul_rn(gamma_lam, carry));
           next_value = v;
-          x[lane][j] = carry;
-          y[lane][j] = __fadd_rn(carry, v);
+          xs[j] = carry;
+          ys[j] = __fadd_rn(carry, v);
         } else {
-          const float ret = __fadd_rn(x[lane][j], __fmul_rn(gamma, carry));
-          carry = __fmul_rn(ret, y[lane][j]);
-          y[lane][j] = ret;
+          const float ret = __fadd_rn(xs[j], __fmul_rn(gamma, carry));
+          carry = __fmul_rn(ret, ys[j]);
+          ys[j] = ret;
         }
+      }
+#pragma unroll
+      for (int j = 0; j < kScanTile; ++j) {
+        if (kMode == 0) x[lane][j] = xs[j];
+        y[lane][j] = ys[j];
       }
     }
     __syncwarp();
+    const uint32_t t = t0 + lane;
     if (t < t_len) {
+#pragma unroll 8
       for (uint32_t r = 0; r < nrows; ++r) {
         const size_t idx = static_cast<size_t>(row0 + r) * t_len + t;
-        if (mode == 0) out_a[idx] = x[r][lane];
+        if (kMode == 0) out_a[idx] = x[r][lane];
         out_b[idx] = y[r][lane];
       }
     }
@@ -117,14 +149,14 @@ __global__ void masked_centered_sq_kernel(const float* __restrict__ x, const voi
                                           size_t n, double* __restrict__ acc) {
   const float mean = whiten_mean(acc, 1e-8f);  // masked_var calls masked_mean with its default eps
   float v[1] = {0.f};
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const float m = load_mask(mask, mask_dtype, i);
-    if (m != 0.f) {
-      const float d = x[i] - mean;
-      v[0] += d * d * m;
-    }
-  }
+  batched_grid_stride<kEwBatch>(
+      n, [&](size_t i) { return make_float2(x[i], load_mask(mask, mask_dtype, i)); },
+      [&](size_t, const float2& in) {
+        if (in.y != 0.f) {
+          const float d = in.x - mean;
+          v[0] += d * d * in.y;
+        }
+      });
   const int slot[1] = {2};
   block_accumulate<1>(v, acc, slot);
 }
@@ -146,9 +178,8 @@ __global__ void whiten_apply_kernel(const float* __restrict__ x, size_t n, const
                                     float* __restrict__ out) {
   const float mean = whiten_mean(acc, 1e-8f);
   const float scale = __fdiv_rn(1.f, __fsqrt_rn(whiten_var(acc, 1) + eps));
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x)
-    out[i] = (x[i] - mean) * scale;
+  batched_grid_stride<2 * kEwBatch>(
+      n, [&](size_t i) { return x[i]; }, [&](size_t i, float xi) { out[i] = (xi - mean) * scale; });
 }
 
 // ------------------------------------------------------------------------------------------ value loss
@@ -159,25 +190,36 @@ __global__ void value_loss_kernel(const float* __restrict__ vpreds, const float*
                                   size_t n, float cliprange, double* __restrict__ acc, float* __restrict__ dvpreds) {
   const float wnorm = 0.5f / (static_cast<float>(acc[0]) + 1e-8f);
   float v[2] = {0.f, 0.f};
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const float m = load_mask(mask, mask_dtype, i);
-    const float vp = vpreds[i], ret = returns[i], old = values[i];
-    const float lo = old - cliprange, hi = old + cliprange;
-    const float vc = fminf(fmaxf(vp, lo), hi);
-    const bool in_range = vp >= lo && vp <= hi;
-    const float e1 = vp - ret, e2 = vc - ret;
-    const float l1 = e1 * e1, l2 = e2 * e2;
-    if (m != 0.f) {
-      v[0] += fmaxf(l1, l2) * m;
-      v[1] += (l1 < l2) ? m : 0.f;
-    }
-    if (dvpreds) {
-      const float d1 = 2.f * e1, d2 = in_range ? 2.f * e2 : 0.f;
-      const float d = (l1 > l2) ? d1 : ((l1 < l2) ? d2 : 0.5f * d1 + 0.5f * d2);  // torch.max splits ties evenly
-      dvpreds[i] = (m != 0.f) ? m * wnorm * d : 0.f;
-    }
-  }
+  struct In {
+    float m, vp, ret, old;
+  };
+  batched_grid_stride<kEwBatch>(
+      n,
+      [&](size_t i) {
+        In in;
+        in.m = load_mask(mask, mask_dtype, i);
+        in.vp = vpreds[i];
+        in.ret = returns[i];
+        in.old = values[i];
+        return in;
+      },
+      [&](size_t i, const In& in) {
+        const float m = in.m, vp = in.vp;
+        const float lo = in.old - cliprange, hi = in.old + cliprange;
+        const float vc = fminf(fmaxf(vp, lo), hi);
+        const bool in_range = vp >= lo && vp <= hi;
+        const float e1 = vp - in.ret, e2 = vc - in.ret;
+        const float l1 = e1 * e1, l2 = e2 * e2;
+        if (m != 0.f) {
+          v[0] += fmaxf(l1, l2) * m;
+          v[1] += (l1 < l2) ? m : 0.f;
+        }
+        if (dvpreds) {
+          const float d1 = 2.f * e1, d2 = in_range ? 2.f * e2 : 0.f;
+          const float d = (l1 > l2) ? d1 : ((l1 < l2) ? d2 : 0.5f * d1 + 0.5f * d2);  // torch.max splits ties evenly
+          dvpreds[i] = (m != 0.f) ? m * wnorm * d : 0.f;
+        }
+      });
   const int slot[2] = {1, 2};
   block_accumulate<2>(v, acc, slot);
 }

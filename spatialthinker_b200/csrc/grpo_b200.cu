@@ -532,6 +532,12 @@ static LossCfg make_loss_cfg(float clip_lo, float clip_hi, float clip_dual, int 
   c.inv_grad_accum = 1.f / grad_accum;
   return c;
 }
+// grid of broadcast_adv_kernel: up to 4 x 256 columns per block and pass, rows folded onto gridDim.y
+static inline dim3 bcast_grid(int64_t bsz, int64_t t_len) {
+  const int64_t gx = (t_len + 1023) / 1024;
+  const int64_t cap = (148 * 8 * 4 + gx - 1) / gx;  // a few waves of blocks, then rows are looped over
+  return dim3(static_cast<unsigned>(gx), static_cast<unsigned>(bsz < cap ? bsz : cap));
+}
 static inline uint32_t ew_blocks(int64_t n, int threads, int sms) {
   const int64_t want = (n + threads - 1) / threads;
   const int64_t cap = static_cast<int64_t>(sms > 0 ? sms : 148) * 8;
@@ -806,7 +812,7 @@ int grpo_advantage_from_scores(const float* scores_all, const int32_t* order, co
                                                                    static_cast<uint32_t>(n_groups), eps, seq_scratch);
   count_launch();
   if (bsz_local > 0 && t_len > 0) {
-    broadcast_adv_kernel<<<ew_blocks(bsz_local * t_len, 256, 0), 256, 0, stream>>>(
+    broadcast_adv_kernel<<<bcast_grid(bsz_local, t_len), 256, 0, stream>>>(
         seq_scratch + row_begin, mask, mask_dtype, static_cast<uint32_t>(bsz_local), static_cast<uint32_t>(t_len),
         advantages);
     count_launch();
@@ -833,7 +839,7 @@ int grpo_advantage(const float* rewards, const void* mask, int mask_dtype, const
   group_stats_kernel<<<cdiv(n_groups * 32, 256), 256, 0, stream>>>(scores, order, offsets,
                                                                    static_cast<uint32_t>(n_groups), eps, seq_adv);
   count_launch();
-  broadcast_adv_kernel<<<ew_blocks(bsz * t_len, 256, 0), 256, 0, stream>>>(seq_adv, mask, mask_dtype, b, t,
+  broadcast_adv_kernel<<<bcast_grid(bsz, t_len), 256, 0, stream>>>(seq_adv, mask, mask_dtype, b, t,
                                                                            advantages);
   count_launch();
   GRPO_CUDA(cudaGetLastError());
@@ -862,7 +868,7 @@ int grpo_rloo_advantage(const float* rewards, const void* mask, int mask_dtype, 
   row_score_kernel<<<cdiv(bsz * 32, 256), 256, 0, stream>>>(rewards, b, t, scores);
   group_rloo_kernel<<<cdiv(n_groups * 32, 256), 256, 0, stream>>>(scores, order, offsets,
                                                                   static_cast<uint32_t>(n_groups), seq_adv);
-  broadcast_adv_kernel<<<ew_blocks(bsz * t_len, 256, 0), 256, 0, stream>>>(seq_adv, mask, mask_dtype, b, t,
+  broadcast_adv_kernel<<<bcast_grid(bsz, t_len), 256, 0, stream>>>(seq_adv, mask, mask_dtype, b, t,
                                                                            advantages);
   count_launch(3);
   GRPO_CUDA(cudaGetLastError());
@@ -880,7 +886,7 @@ int grpo_remax_advantage(const float* rewards, const float* reward_baselines, co
   const uint32_t b = static_cast<uint32_t>(bsz), t = static_cast<uint32_t>(t_len);
   row_score_kernel<<<cdiv(bsz * 32, 256), 256, 0, stream>>>(rewards, b, t, scores);
   remax_seq_kernel<<<cdiv(bsz, 256), 256, 0, stream>>>(scores, reward_baselines, b, seq_adv);
-  broadcast_adv_kernel<<<ew_blocks(bsz * t_len, 256, 0), 256, 0, stream>>>(seq_adv, mask, mask_dtype, b, t,
+  broadcast_adv_kernel<<<bcast_grid(bsz, t_len), 256, 0, stream>>>(seq_adv, mask, mask_dtype, b, t,
                                                                            advantages);
   count_launch(3);
   GRPO_CUDA(cudaGetLastError());
@@ -935,9 +941,24 @@ int grpo_reinforce_pp_advantage(const float* rewards, const void* mask, int mask
     return fail(GRPO_ERR_ARG, "rewards / advantages / returns / acc_scratch must not be null");
   GRPO_TRY(check_seq_args(mask, mask_dtype, bsz, t_len));
   if (bsz == 0 || t_len == 0) return 0;
-  reverse_scan_kernel<<<cdiv(bsz, kScanTile * kScanWarps), kScanWarps * 32, 0, stream>>>(
-      1, rewards, nullptr, mask, mask_dtype, static_cast<uint32_t>(bsz), static_cast<uint32_t>(t_len), gamma, 0.f,
-      nullptr, returns);
+  const uint32_t sb = cdiv(bsz, kScanTile), b32 = static_cast<uint32_t>(bsz), t32 = static_cast<uint32_t>(t_len);
+  switch (mask_dtype) {
+    case MASK_I64:
+      reverse_scan_kernel<1, long long, true><<<sb, 32, 0, stream>>>(rewards, nullptr, static_cast<const long long*>(mask), b32,
+                                                               t32, gamma, 0.f, nullptr, returns);
+      break;
+    case MASK_U8:
+      reverse_scan_kernel<1, unsigned char, true><<<sb, 32, 0, stream>>>(rewards, nullptr, static_cast<const unsigned char*>(mask),
+                                                                   b32, t32, gamma, 0.f, nullptr, returns);
+      break;
+    case MASK_F32:
+      reverse_scan_kernel<1, float, true><<<sb, 32, 0, stream>>>(rewards, nullptr, static_cast<const float*>(mask), b32, t32,
+                                                                 gamma, 0.f, nullptr, returns);
+      break;
+    default:  // no mask: all ones
+      reverse_scan_kernel<1, float, false><<<sb, 32, 0, stream>>>(rewards, nullptr, nullptr, b32, t32, gamma, 0.f, nullptr,
+                                                                  returns);
+  }
   count_launch();
   GRPO_TRY(whiten_launch(returns, mask, mask_dtype, bsz * t_len, 1e-8f, advantages, acc_scratch, stream));
   GRPO_CUDA(cudaGetLastError());
@@ -951,9 +972,9 @@ int grpo_gae_advantage(const float* rewards, const float* values, const void* ma
     return fail(GRPO_ERR_ARG, "rewards / values / advantages / returns / acc_scratch must not be null");
   GRPO_TRY(check_seq_args(mask, mask_dtype, bsz, t_len));
   if (bsz == 0 || t_len == 0) return 0;
-  reverse_scan_kernel<<<cdiv(bsz, kScanTile * kScanWarps), kScanWarps * 32, 0, stream>>>(
-      0, rewards, values, nullptr, MASK_NONE, static_cast<uint32_t>(bsz), static_cast<uint32_t>(t_len), gamma,
-      gamma_lam, advantages, returns);
+  reverse_scan_kernel<0, float, false><<<cdiv(bsz, kScanTile), 32, 0, stream>>>(
+      rewards, values, nullptr, static_cast<uint32_t>(bsz), static_cast<uint32_t>(t_len), gamma, gamma_lam, advantages,
+      returns);
   count_launch();
   GRPO_TRY(whiten_launch(advantages, mask, mask_dtype, bsz * t_len, 1e-8f, advantages, acc_scratch, stream));
   GRPO_CUDA(cudaGetLastError());
@@ -1089,25 +1110,24 @@ int grpo_logprob_from_logits(const void* logits, int logits_dtype, const int64_t
   if (rows < 0 || vocab <= 0 || ld < vocab || rows > 0x7fffffffll || vocab > 0x7fffffffll)
     return fail(GRPO_ERR_ARG, "bad dimensions");
   const uint32_t r = static_cast<uint32_t>(rows), v = static_cast<uint32_t>(vocab);
-  const int threads = vocab >= 8192 ? 512 : 128;
+  const int threads = vocab >= 8192 ? 256 : 128;  // eight resident row-blocks per SM hide each other's reduction tails
+#define GRPO_LOGITS_FWD(T, E)                                                                                       \
+  logprob_from_logits_kernel<T, E><<<r, threads, 0, stream>>>(static_cast<const T*>(logits), labels, r, v, ld, logp, \
+                                                              entropy, lse)
   switch (logits_dtype) {
     case LOGITS_F32:
-      logprob_from_logits_kernel<float><<<r, threads, 0, stream>>>(static_cast<const float*>(logits), labels, r, v, ld,
-                                                                   logp, entropy, lse);
-      count_launch();
+      if (entropy) GRPO_LOGITS_FWD(float, true); else GRPO_LOGITS_FWD(float, false);
       break;
     case LOGITS_BF16:
-      logprob_from_logits_kernel<__nv_bfloat16><<<r, threads, 0, stream>>>(
-          static_cast<const __nv_bfloat16*>(logits), labels, r, v, ld, logp, entropy, lse);
-      count_launch();
+      if (entropy) GRPO_LOGITS_FWD(__nv_bfloat16, true); else GRPO_LOGITS_FWD(__nv_bfloat16, false);
       break;
     case LOGITS_F16:
-      logprob_from_logits_kernel<__half><<<r, threads, 0, stream>>>(static_cast<const __half*>(logits), labels, r, v,
-                                                                    ld, logp, entropy, lse);
-      count_launch();
+      if (entropy) GRPO_LOGITS_FWD(__half, true); else GRPO_LOGITS_FWD(__half, false);
       break;
     default: return fail(GRPO_ERR_ARG, "unknown logits dtype %d", logits_dtype);
   }
+#undef GRPO_LOGITS_FWD
+  count_launch();
   GRPO_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1123,28 +1143,30 @@ int grpo_logprob_from_logits_bwd(const void* logits, int logits_dtype, const int
     return fail(GRPO_ERR_ARG, "bad dimensions");
   if (rows == 0) return 0;
   const uint32_t r = static_cast<uint32_t>(rows), v = static_cast<uint32_t>(vocab);
-  dim3 grid(cdiv(vocab, 256 * 8), r < 65535u ? r : 65535u);
+  const size_t esz = logits_dtype == LOGITS_F32 ? 4 : 2;
+  const int64_t vec = 16 / static_cast<int64_t>(esz);
+  const bool vector = vocab % vec == 0 && ld % vec == 0 && ld_out % vec == 0 &&
+                      (reinterpret_cast<uintptr_t>(logits) & 15u) == 0 && (reinterpret_cast<uintptr_t>(dlogits) & 15u) == 0;
+  // four 16-byte vectors (or 8 scalars) per thread: the per-row constants are amortised, the grid stays in the 1e5 range
+  dim3 grid(cdiv(vocab, 256 * (vector ? 4 * vec : 8)), r < 65535u ? r : 65535u);
+#define GRPO_LOGITS_BWD(T, V)                                                                                         \
+  logprob_from_logits_bwd_kernel<T, V><<<grid, 256, 0, stream>>>(static_cast<const T*>(logits), labels, lse, dlogp,    \
+                                                                 dentropy, entropy, r, v, ld, static_cast<T*>(dlogits), \
+                                                                 ld_out)
   switch (logits_dtype) {
     case LOGITS_F32:
-      logprob_from_logits_bwd_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(logits), labels, lse,
-                                                                      dlogp, dentropy, entropy, r, v, ld,
-                                                                      static_cast<float*>(dlogits), ld_out);
-      count_launch();
+      if (vector) GRPO_LOGITS_BWD(float, true); else GRPO_LOGITS_BWD(float, false);
       break;
     case LOGITS_BF16:
-      logprob_from_logits_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(
-          static_cast<const __nv_bfloat16*>(logits), labels, lse, dlogp, dentropy, entropy, r, v, ld,
-          static_cast<__nv_bfloat16*>(dlogits), ld_out);
-      count_launch();
+      if (vector) GRPO_LOGITS_BWD(__nv_bfloat16, true); else GRPO_LOGITS_BWD(__nv_bfloat16, false);
       break;
     case LOGITS_F16:
-      logprob_from_logits_bwd_kernel<__half><<<grid, 256, 0, stream>>>(static_cast<const __half*>(logits), labels, lse,
-                                                                       dlogp, dentropy, entropy, r, v, ld,
-                                                                       static_cast<__half*>(dlogits), ld_out);
-      count_launch();
+      if (vector) GRPO_LOGITS_BWD(__half, true); else GRPO_LOGITS_BWD(__half, false);
       break;
     default: return fail(GRPO_ERR_ARG, "unknown logits dtype %d", logits_dtype);
   }
+#undef GRPO_LOGITS_BWD
+  count_launch();
   GRPO_CUDA(cudaGetLastError());
   return 0;
 }

@@ -47,8 +47,38 @@ __device__ __forceinline__ OnlineStat stat_merge(const OnlineStat& a, const Onli
   return r;
 }
 
-// one block per row
-template <typename T>
+// A vector of logits at once: one max, at most one rescale of the running sums, then kVec exponentials with no
+// data-dependent branch per element (the scalar form above diverges on every new maximum and spends a second
+// exponential on it).
+template <int kVec, bool kWantT>
+__device__ __forceinline__ void stat_push_vec(OnlineStat& a, const float (&z)[kVec]) {
+  float mx = z[0];
+#pragma unroll
+  for (int k = 1; k < kVec; ++k) mx = fmaxf(mx, z[k]);
+  if (mx == -INFINITY) return;
+  if (mx > a.m) {
+    const float w = (a.m == -INFINITY) ? 0.f : __expf(a.m - mx);
+    a.s *= w;
+    a.t *= w;
+    a.m = mx;
+  }
+#pragma unroll
+  for (int k = 0; k < kVec; ++k) {
+    const float e = __expf(z[k] - a.m);  // exp(-inf) = 0 for masked-out logits
+    a.s += e;
+    if (kWantT && z[k] != -INFINITY) a.t = fmaf(e, z[k], a.t);  // sum e * z, only needed for the entropy
+  }
+}
+
+template <typename T, int kVec>
+__device__ __forceinline__ void unpack_vec(const uint4& q, float (&z)[kVec]) {
+  const T* e = reinterpret_cast<const T*>(&q);
+#pragma unroll
+  for (int k = 0; k < kVec; ++k) z[k] = to_f32<T>(e[k]);
+}
+
+// one block per row; 16-byte loads, four of them in flight per thread. kWantT: also carry sum exp(z) * z (entropy).
+template <typename T, bool kWantT>
 __global__ void logprob_from_logits_kernel(const T* __restrict__ logits, const int64_t* __restrict__ labels,
                                            uint32_t rows, uint32_t vocab, int64_t ld, float* __restrict__ logp,
                                            float* __restrict__ entropy, float* __restrict__ lse_out) {
@@ -60,11 +90,24 @@ __global__ void logprob_from_logits_kernel(const T* __restrict__ logits, const i
   const bool vec_ok = ((reinterpret_cast<uintptr_t>(z) & 15u) == 0) && (vocab % kVec == 0);
   if (vec_ok) {
     const uint4* z4 = reinterpret_cast<const uint4*>(z);
-    for (uint32_t i = threadIdx.x; i < vocab / kVec; i += blockDim.x) {
-      const uint4 q = z4[i];
-      const T* e = reinterpret_cast<const T*>(&q);
-#pragma unroll
-      for (int k = 0; k < kVec; ++k) stat_push(st, to_f32<T>(e[k]));
+    const uint32_t nvec = vocab / kVec, step = blockDim.x;
+    uint32_t i = threadIdx.x;
+    for (; i + 3 * step < nvec; i += 4 * step) {
+      const uint4 q0 = __ldcs(z4 + i), q1 = __ldcs(z4 + i + step), q2 = __ldcs(z4 + i + 2 * step), q3 = __ldcs(z4 + i + 3 * step);
+      float f[kVec];
+      unpack_vec<T, kVec>(q0, f);
+      stat_push_vec<kVec, kWantT>(st, f);
+      unpack_vec<T, kVec>(q1, f);
+      stat_push_vec<kVec, kWantT>(st, f);
+      unpack_vec<T, kVec>(q2, f);
+      stat_push_vec<kVec, kWantT>(st, f);
+      unpack_vec<T, kVec>(q3, f);
+      stat_push_vec<kVec, kWantT>(st, f);
+    }
+    for (; i < nvec; i += step) {
+      float f[kVec];
+      unpack_vec<T, kVec>(__ldcs(z4 + i), f);
+      stat_push_vec<kVec, kWantT>(st, f);
     }
   } else {
     for (uint32_t i = threadIdx.x; i < vocab; i += blockDim.x) stat_push(st, to_f32<T>(z[i]));
@@ -104,12 +147,23 @@ __global__ void logprob_from_logits_kernel(const T* __restrict__ logits, const i
 }
 
 // dlogits[r][v] = dlogp[r] * (1[v == label] - softmax(z_r)[v]) + dent[r] * (-p (log p + H))   (dent optional)
-template <typename T>
+__device__ __forceinline__ float dlogit_value(float zi, float l, float g, float ge, float h, bool is_label) {
+  const float lp = zi - l;
+  const float p = __expf(lp);
+  float d = -g * p;
+  if (is_label) d += g;
+  if (ge != 0.f && p > 0.f) d -= ge * p * (lp + h);
+  return d;
+}
+
+// grid (column blocks, rows); kVector: 16-byte loads and stores (rows 16-byte aligned, vocab a multiple of the vector)
+template <typename T, bool kVector>
 __global__ void logprob_from_logits_bwd_kernel(const T* __restrict__ logits, const int64_t* __restrict__ labels,
                                                const float* __restrict__ lse, const float* __restrict__ dlogp,
                                                const float* __restrict__ dent, const float* __restrict__ ent,
                                                uint32_t rows, uint32_t vocab, int64_t ld, T* __restrict__ dlogits,
                                                int64_t ld_out) {
+  constexpr int kVec = 16 / sizeof(T);
   for (uint32_t r = blockIdx.y; r < rows; r += gridDim.y) {
     const T* z = logits + static_cast<int64_t>(r) * ld;
     T* o = dlogits + static_cast<int64_t>(r) * ld_out;
@@ -118,14 +172,22 @@ __global__ void logprob_from_logits_bwd_kernel(const T* __restrict__ logits, con
     const float h = (dent && ent) ? ent[r] : 0.f;
     const float l = lse[r];
     const int64_t lab = labels ? labels[r] : -1;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < vocab; i += gridDim.x * blockDim.x) {
-      const float zi = to_f32<T>(z[i]);
-      const float lp = zi - l;
-      const float p = __expf(lp);
-      float d = -g * p;
-      if (static_cast<int64_t>(i) == lab) d += g;
-      if (ge != 0.f && p > 0.f) d -= ge * p * (lp + h);
-      o[i] = from_f32<T>(d);
+    if (kVector) {
+      const uint4* z4 = reinterpret_cast<const uint4*>(z);
+      uint4* o4 = reinterpret_cast<uint4*>(o);
+      for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < vocab / kVec; i += gridDim.x * blockDim.x) {
+        const uint4 q = z4[i];  // may alias o4[i] (in-place backward): plain load, read before the store below
+        const T* e = reinterpret_cast<const T*>(&q);
+        uint4 w;
+        T* d = reinterpret_cast<T*>(&w);
+        const int64_t c0 = static_cast<int64_t>(i) * kVec;
+#pragma unroll
+        for (int k = 0; k < kVec; ++k) d[k] = from_f32<T>(dlogit_value(to_f32<T>(e[k]), l, g, ge, h, c0 + k == lab));
+        o4[i] = w;
+      }
+    } else {
+      for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < vocab; i += gridDim.x * blockDim.x)
+        o[i] = from_f32<T>(dlogit_value(to_f32<T>(z[i]), l, g, ge, h, static_cast<int64_t>(i) == lab));
     }
   }
 }

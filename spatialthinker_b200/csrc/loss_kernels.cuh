@@ -49,6 +49,28 @@ __device__ __forceinline__ float load_mask(const void* m, int dtype, size_t i) {
   }
 }
 
+// Grid-stride loop with kBatch iterations in flight: every load of a batch is issued before the first use, so each
+// thread keeps kBatch x (number of input streams) independent requests outstanding - the memory-level parallelism a
+// 4-byte-per-thread elementwise kernel needs to cover HBM latency at 148 SMs x 2048 threads.
+//   ld(i) -> In (all global loads of element i)      use(i, in) (arithmetic + stores of element i)
+template <int kBatch, class Ld, class Use>
+__device__ __forceinline__ void batched_grid_stride(size_t n, Ld&& ld, Use&& use) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  for (; i + (kBatch - 1) * stride < n; i += kBatch * stride) {
+    decltype(ld(i)) in[kBatch];
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) in[u] = ld(i + u * stride);
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) use(i + u * stride, in[u]);
+  }
+  for (; i < n; i += stride) {
+    const auto in = ld(i);
+    use(i, in);
+  }
+}
+constexpr int kEwBatch = 4;
+
 // value and d/dlogp of one KL estimator (core_algos.py:408-434)
 __device__ __forceinline__ void kl_term(int mode, float logp, float ref, float& val, float& dlogp) {
   switch (mode) {
@@ -137,9 +159,8 @@ __device__ __forceinline__ void block_accumulate(float (&v)[N], double* acc, con
 // acc[ACC_MASK] += sum(mask)
 __global__ void mask_sum_kernel(const void* __restrict__ mask, int mask_dtype, size_t n, double* __restrict__ acc) {
   float v[1] = {0.f};
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x)
-    v[0] += load_mask(mask, mask_dtype, i);
+  batched_grid_stride<2 * kEwBatch>(
+      n, [&](size_t i) { return load_mask(mask, mask_dtype, i); }, [&](size_t, float m) { v[0] += m; });
   const int slot[1] = {ACC_MASK};
   block_accumulate<1>(v, acc, slot);
 }
@@ -155,26 +176,40 @@ __global__ void token_loss_kernel(const float* __restrict__ logp, const float* _
   const float denom = static_cast<float>(acc[ACC_MASK]) + 1e-8f;
   const float wnorm = cfg.inv_grad_accum / denom;
   float v[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const float m = load_mask(mask, mask_dtype, i);
-    const float lp = logp[i];
-    float loss, dpg, cfh, cfl, x;
-    pg_term(cfg, lp, old_logp[i], adv[i], loss, dpg, cfh, cfl, x);
-    float klv = 0.f, dkl = 0.f;
-    if (cfg.kl_mode != KL_NONE && ref_logp != nullptr) kl_term(cfg.kl_mode, lp, ref_logp[i], klv, dkl);
-    if (m != 0.f) {  // reference multiplies by the mask: garbage at padded positions never contributes
-      v[0] += loss * m;
-      v[1] += cfh * m;
-      v[2] += cfl * m;
-      v[3] += -x * m;
-      v[4] += klv * m;
-      v[5] += lp * m;
-      if (entropy) v[6] += entropy[i] * m;
-    }
-    if (dlogp_out) dlogp_out[i] = (m != 0.f) ? m * wnorm * (dpg + cfg.kl_coef * dkl) : 0.f;
-    if (dent_out) dent_out[i] = (m != 0.f) ? -cfg.entropy_coef * m * wnorm : 0.f;
-  }
+  struct In {
+    float m, lp, old, adv, ref, ent;
+  };
+  const bool use_kl = cfg.kl_mode != KL_NONE && ref_logp != nullptr;
+  batched_grid_stride<kEwBatch>(
+      n,
+      [&](size_t i) {
+        In in;
+        in.m = load_mask(mask, mask_dtype, i);
+        in.lp = logp[i];
+        in.old = old_logp[i];
+        in.adv = adv[i];
+        in.ref = use_kl ? ref_logp[i] : 0.f;
+        in.ent = entropy ? entropy[i] : 0.f;
+        return in;
+      },
+      [&](size_t i, const In& in) {
+        const float m = in.m, lp = in.lp;
+        float loss, dpg, cfh, cfl, x;
+        pg_term(cfg, lp, in.old, in.adv, loss, dpg, cfh, cfl, x);
+        float klv = 0.f, dkl = 0.f;
+        if (use_kl) kl_term(cfg.kl_mode, lp, in.ref, klv, dkl);
+        if (m != 0.f) {  // reference multiplies by the mask: garbage at padded positions never contributes
+          v[0] += loss * m;
+          v[1] += cfh * m;
+          v[2] += cfl * m;
+          v[3] += -x * m;
+          v[4] += klv * m;
+          v[5] += lp * m;
+          if (entropy) v[6] += in.ent * m;
+        }
+        if (dlogp_out) dlogp_out[i] = (m != 0.f) ? m * wnorm * (dpg + cfg.kl_coef * dkl) : 0.f;
+        if (dent_out) dent_out[i] = (m != 0.f) ? -cfg.entropy_coef * m * wnorm : 0.f;
+      });
   const int slot[7] = {ACC_PG, ACC_CF_HI, ACC_CF_LO, ACC_NEG_X, ACC_KL, ACC_LOGP, ACC_ENT};
   block_accumulate<7>(v, acc, slot);
 }
@@ -202,25 +237,26 @@ __global__ void loss_finalize_kernel(const double* __restrict__ acc, LossCfg cfg
 // Elementwise KL estimator with its derivative (standalone compute_kl surface).
 __global__ void kl_elementwise_kernel(const float* __restrict__ logp, const float* __restrict__ ref, size_t n, int mode,
                                       float* __restrict__ out, float* __restrict__ dout_dlogp) {
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    float v, d;
-    kl_term(mode, logp[i], ref[i], v, d);
-    out[i] = v;
-    if (dout_dlogp) dout_dlogp[i] = d;
-  }
+  batched_grid_stride<kEwBatch>(
+      n, [&](size_t i) { return make_float2(logp[i], ref[i]); },
+      [&](size_t i, const float2& in) {
+        float v, d;
+        kl_term(mode, in.x, in.y, v, d);
+        out[i] = v;
+        if (dout_dlogp) dout_dlogp[i] = d;
+      });
 }
 
 // masked_mean over all elements: out[0] = sum(x*mask) / (sum(mask) + eps)
 __global__ void masked_sum_kernel(const float* __restrict__ x, const void* __restrict__ mask, int mask_dtype, size_t n,
                                   double* __restrict__ acc /*[2]: sum(x*m), sum(m)*/) {
   float v[2] = {0.f, 0.f};
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const float m = load_mask(mask, mask_dtype, i);
-    if (m != 0.f) v[0] += x[i] * m;
-    v[1] += m;
-  }
+  batched_grid_stride<kEwBatch>(
+      n, [&](size_t i) { return make_float2(x[i], load_mask(mask, mask_dtype, i)); },
+      [&](size_t, const float2& in) {
+        if (in.y != 0.f) v[0] += in.x * in.y;  // a masked-out value may be anything, NaN included
+        v[1] += in.y;
+      });
   const int slot[2] = {0, 1};
   block_accumulate<2>(v, acc, slot);
 }
