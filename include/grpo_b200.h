@@ -38,7 +38,7 @@ typedef struct CUstream_st* grpo_stream_t;
 #define GRPO_KL_CHI2 4    /* "chi2" */
 
 /* metric slots written by the loss entry points (float[GRPO_NUM_METRICS], device memory) -
- * the actor/* keys of verl/workers/actor/dp_actor.py:274-286 */
+ * the "actor/..." keys of verl/workers/actor/dp_actor.py:274-286 */
 #define GRPO_MET_PG_LOSS 0     /* masked_mean(policy loss), before the KL term   core_algos.py:349 */
 #define GRPO_MET_CLIPFRAC_HI 1 /* actor/pg_clipfrac_higher                        core_algos.py:350 */
 #define GRPO_MET_CLIPFRAC_LO 2 /* actor/pg_clipfrac_lower                         core_algos.py:351 */

@@ -169,3 +169,28 @@ def test_patch_verl_roundtrip(reference_modules):
     finally:
         st.unpatch_verl()
     assert ca.compute_policy_loss is orig
+
+
+def test_header_is_plain_c_and_links(lib, tmp_path):
+    """The boundary is a C ABI: include/grpo_b200.h must compile as C99 and a plain C program must link against the
+    library and get answers from its host-only entry points (no CUDA device needed for these)."""
+    from spatialthinker_b200 import _lib
+
+    src = tmp_path / "abi.c"
+    src.write_text(
+        '#include "grpo_b200.h"\n#include <stdio.h>\n'
+        "int main(void) {\n"
+        "  size_t ws = grpo_fused_loss_workspace_bytes(37888, 3584, 151936);\n"
+        "  int rc = grpo_compute_kl(0, 0, 4, GRPO_KL_LOW_VAR, 0, 0, 0); /* null pointers: argument error, not a crash */\n"
+        '  printf("%d %zu %d %s\\n", grpo_abi_version(), ws, rc, grpo_last_error());\n'
+        "  return 0;\n}\n")
+    exe = tmp_path / "abi"
+    cc = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src),
+                         "-o", str(exe), _lib.LIB_PATH, "-Wl,-rpath," + os.path.dirname(_lib.LIB_PATH)],
+                        capture_output=True, text=True)
+    assert cc.returncode == 0, cc.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0, out.stderr
+    version, ws, rc, msg = out.stdout.split(maxsplit=3)
+    assert int(version) == 1 and int(ws) == lib.grpo_fused_loss_workspace_bytes(37888, 3584, 151936)
+    assert int(rc) == -1 and "null" in msg
