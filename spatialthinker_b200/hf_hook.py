@@ -5,8 +5,9 @@ The reference's actor calls the full model and slices the LOGITS (``logits[:, -T
 packed equivalent :118-139), which materialises ``[tokens, vocab]`` for prompt and response alike. The fused head only
 needs ``hidden[:, -T-1:-1]`` - ``T`` rows per sequence - and ``lm_head.weight``.
 
-Only the padded (non ``padding_free``) layout is handled here; the packed layout needs the reference's flash-attn varlen
-patch (``verl/models/monkey_patch.py``), which is outside this path.
+Two layouts, as in the reference: padded ``[bsz, seqlen, H]`` (:func:`response_hidden_states`) and ``padding_free``
+packed ``[total_nnz, H]`` (:func:`packed_response_hidden_states`, dp_actor.py:85-139: the body runs on the unpadded token
+stream through the reference's flash-attn varlen patch, which stays the reference's - ``verl/models/monkey_patch.py``).
 """
 from __future__ import annotations
 
@@ -42,6 +43,54 @@ def response_hidden_states(model: torch.nn.Module, input_ids: torch.Tensor, atte
                                   use_cache=False, **model_kwargs)
     hidden = out.last_hidden_state if hasattr(out, "last_hidden_state") else out[0]
     return hidden[:, -response_length - 1: -1]
+
+
+class _PackedResponseRows(torch.autograd.Function):
+    """Rows of a packed ``[total_nnz, H]`` hidden-state stream that predict the response tokens, as ``[bsz, T, H]``.
+
+    The reference pads the per-token LOG-PROBS back to ``(bsz, seqlen)`` (``pad_input``, dp_actor.py:134-138) and slices
+    ``[:, -T-1:-1]`` (:139); here the same index map is applied to the HIDDEN rows before the head, so only ``bsz * T``
+    rows reach it. Index map and row moves are this library's kernels (``grpo_compact_index`` / ``grpo_scatter_rows``);
+    positions whose ``attention_mask`` is 0 give zero rows (their ``response_mask`` is 0 too), nothing synchronises.
+    """
+
+    @staticmethod
+    def forward(ctx, hidden_packed, attention_mask, response_length: int):
+        from .fused import compact_index, scatter_rows
+
+        bsz, seqlen = attention_mask.shape
+        t_len = int(response_length)
+        if not 0 < t_len < seqlen:
+            raise ValueError(f"response_length {t_len} does not fit a sequence length of {seqlen}")
+        gather_idx, inverse, _ = compact_index(attention_mask)  # packed <-> (bsz * seqlen) slot maps
+        rows = inverse.view(bsz, seqlen)[:, seqlen - t_len - 1: seqlen - 1].contiguous().view(-1)
+        out = scatter_rows(hidden_packed, rows)  # out[slot] = hidden_packed[rows[slot]] or 0
+        ctx.save_for_backward(gather_idx)
+        ctx.dims = (bsz, seqlen, t_len, hidden_packed.shape[0])
+        return out.view(bsz, t_len, hidden_packed.shape[-1])
+
+    @staticmethod
+    def backward(ctx, grad):
+        from .fused import scatter_rows
+
+        (gather_idx,) = ctx.saved_tensors
+        bsz, seqlen, t_len, nnz = ctx.dims
+        pos = gather_idx[:nnz].long()  # flattened (sequence, position) of every packed token
+        seq = pos // seqlen
+        t = pos - seq * seqlen - (seqlen - t_len - 1)
+        slot = torch.where((t >= 0) & (t < t_len), seq * t_len + t, torch.full_like(t, -1)).to(torch.int32)
+        d_packed = scatter_rows(grad.reshape(bsz * t_len, -1), slot)  # every packed row is read by at most one slot
+        return d_packed, None, None
+
+
+def packed_response_hidden_states(hidden_packed: torch.Tensor, attention_mask: torch.Tensor,
+                                  response_length: int) -> torch.Tensor:
+    """``padding_free`` layout: ``hidden_packed`` is the body's output on the unpadded token stream
+    (``[total_nnz, H]`` or ``[1, total_nnz, H]``, tokens in ``attention_mask`` order as ``unpad_input`` produces them,
+    dp_actor.py:86-89). Returns ``[bsz, T, H]`` with row ``t`` predicting ``responses[:, t]``; differentiable."""
+    if hidden_packed.dim() == 3:
+        hidden_packed = hidden_packed.squeeze(0)
+    return _PackedResponseRows.apply(hidden_packed.contiguous(), attention_mask, response_length)
 
 
 def make_hidden_fn(model: torch.nn.Module) -> Callable[[Dict[str, Any]], torch.Tensor]:

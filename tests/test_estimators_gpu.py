@@ -219,3 +219,36 @@ def test_experience_pass_matches_oracle(st, dev):
     assert out.batch["token_level_rewards"] is out.batch["token_level_scores"] and metrics == {}
     want_adv, _ = O.compute_grpo_outcome_advantage(roll["token_level_rewards"].clone(), mask, roll["uid"])
     close(out.batch["advantages"], want_adv)
+
+
+def test_packed_response_rows_match_pad_and_slice(st, dev):
+    """padding_free layout (dp_actor.py:85-139): the rows handed to the fused head must be the rows whose log-probs the
+    reference keeps after pad_input + [:, -T-1:-1], and the gradient must land on exactly those packed rows."""
+    from spatialthinker_b200 import hf_hook
+
+    g = torch.Generator().manual_seed(4)
+    bsz, prompt, t_len, h = 5, 11, 9, 64
+    seqlen = prompt + t_len
+    mask = torch.zeros(bsz, seqlen, dtype=torch.int64)
+    for i in range(bsz):  # left-padded prompts, right-padded responses, as the reference's collate produces
+        p_len = int(torch.randint(1, prompt + 1, (1,), generator=g))
+        r_len = int(torch.randint(1, t_len + 1, (1,), generator=g))
+        mask[i, prompt - p_len: prompt + r_len] = 1
+    nnz = int(mask.sum())
+    packed = torch.randn(nnz, h, generator=g).to(torch.bfloat16)
+    # reference semantics in plain torch: pad back to (bsz, seqlen), slice
+    padded = torch.zeros(bsz * seqlen, h, dtype=torch.bfloat16)
+    padded[mask.view(-1).bool()] = packed
+    want = padded.view(bsz, seqlen, h)[:, -t_len - 1: -1]
+    x = packed.to(dev).requires_grad_(True)
+    got = hf_hook.packed_response_hidden_states(x.unsqueeze(0), mask.to(dev), t_len)
+    assert got.shape == (bsz, t_len, h) and torch.equal(got.cpu(), want)
+    # every valid response slot found its row
+    resp_mask = mask[:, -t_len:].bool()
+    assert bool((want.float().abs().sum(-1) > 0)[resp_mask].all())
+    up = torch.randn(bsz, t_len, h, generator=g).to(torch.bfloat16)
+    got.backward(up.to(dev))
+    want_grad = torch.zeros(bsz, seqlen, h, dtype=torch.bfloat16)
+    want_grad[:, -t_len - 1: -1] = up
+    want_grad = want_grad.view(-1, h)[mask.view(-1).bool()]
+    assert torch.equal(x.grad.cpu(), want_grad)
