@@ -335,10 +335,18 @@ def main():
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL's own banner ("NCCL version ...", printed when the box exports
-        # NCCL_DEBUG) goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=dev)
+        # stdout carries exactly one JSON line: NCCL printf()s its banner ("NCCL version ...") when the first communicator
+        # is created, so file descriptor 1 points at stderr until that has happened
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.all_reduce(torch.zeros(1, device=dev))
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     import spatialthinker_b200 as st
     from spatialthinker_b200 import _lib
 
