@@ -155,6 +155,9 @@ def valid_counts(x, plan):
     return {(sl.start, sl.stop): int(lens[sl].sum()) for mbs in plan for sl in mbs}
 
 
+ENTROPY_COEFF = 0.0  # --entropy-coeff: the upstream-veRL entropy bonus (0 in the reference, which only logs the entropy)
+
+
 def run_step_device(st, x, plan, dweight, world, temperature, want_entropy, counts=None):
     from spatialthinker_b200.sharding import allreduce_mean_
 
@@ -168,7 +171,7 @@ def run_step_device(st, x, plan, dweight, world, temperature, want_entropy, coun
         for sl in mbs:
             res = st.grpo_micro_batch_step(x["hidden"][sl], x["weight"], x["labels"][sl], x["old"][sl], adv[sl], x["ref"][sl],
                                            x["mask"][sl], temperature=temperature, grad_accum=ga, dweight_accum=dweight,
-                                           want_entropy=want_entropy,
+                                           want_entropy=want_entropy, entropy_coeff=ENTROPY_COEFF,
                                            valid_rows=None if counts is None else counts[(sl.start, sl.stop)], **CLIP, **KL)
             metrics.append(res["metrics"])
         allreduce_mean_(dweight)
@@ -232,7 +235,7 @@ def run_step_e2e(st, x, feed, plan, dweight, temperature, want_entropy, host_met
         mb = feed.get(slot, sl)
         res = st.grpo_micro_batch_step(mb["hidden"], x["weight"], mb["labels"], mb["old"], mb["adv"], mb["ref"], mb["mask"],
                                        temperature=temperature, grad_accum=float(len(plan[i])), dweight_accum=dweight,
-                                       want_entropy=want_entropy,
+                                       want_entropy=want_entropy, entropy_coeff=ENTROPY_COEFF,
                                        valid_rows=None if counts is None else counts[(sl.start, sl.stop)], **CLIP, **KL)
         feed.release(slot)
         metrics.append(res["metrics"])
@@ -318,9 +321,13 @@ def main():
     ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
     ap.add_argument("--micro-seqs", type=int, default=0, help="sequences per micro-batch (0: 37888 tokens' worth)")
     ap.add_argument("--sequences", type=int, default=0, help="override the rollout batch size (debug)")
+    ap.add_argument("--entropy-coeff", type=float, default=0.0,
+                    help="loss -= coeff * masked_mean(entropy): adds the per-element stash -> dlogits pass (not in the reference)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    global ENTROPY_COEFF
+    ENTROPY_COEFF = args.entropy_coeff
     cfg = list(CONFIGS[args.config])
     if args.sequences:
         cfg[2] = args.sequences
@@ -448,7 +455,7 @@ def main():
         "data": "synthetic",
         "config": {"workload": f"{args.config}: {desc}", "hidden": hdim, "vocab": vocab, "sequences": bsz, "response_len": tlen,
                    "group_n": n, "micro_batch_sequences": micro_seqs, "optimizer_steps_per_step": len(plan),
-                   "loss": "GRPO clip .2/.3/3.0 + low_var_kl 1e-2", "l2": "inputs (>= 30 GB) far exceed the 126 MB L2",
+                   "loss": "GRPO clip .2/.3/3.0 + low_var_kl 1e-2" + (f" - {args.entropy_coeff} * entropy" if args.entropy_coeff else ""), "l2": "inputs (>= 30 GB) far exceed the 126 MB L2",
                    "parallelism": f"dp{world} by sequence, dW mean all-reduce (NCCL)"},
         "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline, "e2e": e2e,
     }

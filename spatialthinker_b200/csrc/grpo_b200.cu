@@ -469,7 +469,7 @@ static int chunk_backward(const DevInfo& dev, const Workspace& w, const __nv_bfl
                                                                   1.f / temperature, un, uh, uv, w.row_scale, w.onehot,
                                                                   w.hd_scaled, dweight);
     } else {
-      dim3 grid(cdiv(v / 8, 256 * 4), un < 65535u ? un : 65535u);
+      dim3 grid(cdiv(cdiv(v, 64), kDlogitsColBlocksPerCta), cdiv(n, 64));  // (runs of column blocks, row blocks)
       stash_to_dlogits_kernel<<<grid, 256, 0, stream>>>(w.stash, static_cast<uint32_t>(w.stash_vb), un, uv, w.inv_sum,
                                                         dlogp, dent, ent, labels + r0, 1.f / temperature);
     }

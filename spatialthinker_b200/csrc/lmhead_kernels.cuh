@@ -402,55 +402,85 @@ __global__ void scale_scatter_kernel(const __nv_bfloat16* __restrict__ hidden, c
 // after which the backward GEMMs run with unit scales. Rows whose upstream gradients are all zero are written as zeros
 // without reading the stash.
 // ------------------------------------------------------------------------------------------
-__global__ void stash_to_dlogits_kernel(__nv_bfloat16* __restrict__ stash, uint32_t stash_vb, uint32_t rows,
-                                        uint32_t vocab, const float* __restrict__ inv_sum,
-                                        const float* __restrict__ dlogp, const float* __restrict__ dent,
-                                        const float* __restrict__ ent, const int64_t* __restrict__ labels,
-                                        float scale) {
-  const uint32_t vecs_per_row = vocab >> 3;
-  for (uint32_t r = blockIdx.y; r < rows; r += gridDim.y) {
-    const float g = dlogp[r] * scale;
-    const float ge = dent ? dent[r] * scale : 0.f;
-    const float h = dent ? ent[r] : 0.f;
-    const float c = inv_sum[r];
-    const float log_c = __logf(c);
-    const int64_t lab = labels[r];
-    // blocked stash: row r lives in row block r/64; its 64-column block b starts b * 4096 elements further on
-    __nv_bfloat16* rowp = stash + static_cast<size_t>(r >> 6) * stash_vb * 4096 + (r & 63) * 64;
-    for (uint32_t vi = blockIdx.x * blockDim.x + threadIdx.x; vi < vecs_per_row; vi += gridDim.x * blockDim.x) {
-      uint4 out = make_uint4(0u, 0u, 0u, 0u);
-      const uint32_t col = vi << 3;
-      uint4* vecp = reinterpret_cast<uint4*>(rowp + static_cast<size_t>(col >> 6) * 4096 + (col & 63));
-      if (g != 0.f || ge != 0.f) {
-        const uint4 in = *vecp;
-        const uint32_t w[4] = {in.x, in.y, in.z, in.w};
-        float f[8];
+// Walks the stash in its storage order: a CTA owns one block of 64 rows and a run of 64-column blocks, each of them 8 KB
+// contiguous in HBM (a row-by-row walk would touch 2374 different 8 KB blocks with 128 bytes each per row). The 64
+// rows' constants sit in shared memory; every thread moves two 16-byte vectors per block, two blocks in flight.
+constexpr int kDlogitsColBlocksPerCta = 8;
+__global__ void __launch_bounds__(256)
+stash_to_dlogits_kernel(__nv_bfloat16* __restrict__ stash, uint32_t stash_vb, uint32_t rows, uint32_t vocab,
+                        const float* __restrict__ inv_sum, const float* __restrict__ dlogp,
+                        const float* __restrict__ dent, const float* __restrict__ ent,
+                        const int64_t* __restrict__ labels, float scale) {
+  // dz = e * (A - B * log2 e) with per-row A = c * (-g - ge * (ln c + H)), B = c * ge * ln 2  (p = c * e, c = 1 / S):
+  // one MUFU and two FMA-pipe operations per element; the one-hot term adds g at the label's column
+  __shared__ float s_g[64], s_a[64], s_b[64];
+  __shared__ int64_t s_lab[64];
+  const uint32_t rb = blockIdx.y;
+  if (threadIdx.x < 64) {
+    const uint32_t r = rb * 64 + threadIdx.x;
+    const bool ok = r < rows;
+    const float c = ok ? inv_sum[r] : 0.f;
+    const float g = ok ? dlogp[r] * scale : 0.f;
+    const float ge = (ok && dent) ? dent[r] * scale : 0.f;
+    const float h = (ok && dent) ? ent[r] : 0.f;
+    s_g[threadIdx.x] = g;
+    s_a[threadIdx.x] = (ge != 0.f) ? c * (-g - ge * (__logf(c) + h)) : -g * c;
+    s_b[threadIdx.x] = c * ge * 0.6931471805599453f;
+    s_lab[threadIdx.x] = ok ? labels[r] : -1;
+  }
+  __syncthreads();
+  const uint32_t n_vb = (vocab + 63) >> 6;  // column blocks that hold real columns (stash_vb may be padded beyond)
+  const uint32_t vb0 = blockIdx.x * kDlogitsColBlocksPerCta;
+  const uint32_t vb1 = min(vb0 + kDlogitsColBlocksPerCta, n_vb);
+  uint4* base = reinterpret_cast<uint4*>(stash + static_cast<size_t>(rb) * stash_vb * 4096);
+  // vector q of a block: row q / 8 of the block, columns (q % 8) * 8 .. + 7
+  auto transform = [&](uint32_t vb, uint32_t q, const uint4& in) {
+    const uint32_t ri = q >> 3;
+    if (vb * 64 + (q & 7) * 8 >= vocab || rb * 64 + ri >= rows) return in;  // padding of the last blocks: left as it is
+    const float g = s_g[ri], a = s_a[ri], b = s_b[ri];
+    uint4 out = make_uint4(0u, 0u, 0u, 0u);
+    if (g != 0.f || b != 0.f) {  // rows without upstream gradient (dlogp = dent = 0) become zeros
+      const uint32_t w[4] = {in.x, in.y, in.z, in.w};
+      float f[8];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          f[2 * i] = __uint_as_float(w[i] << 16);
-          f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float e = f[i];
-          const float p = c * e;
-          float d = -g * p;
-          if (ge != 0.f && e > 0.f) d -= ge * p * (log_c + __logf(e) + h);
-          f[i] = d;
-        }
-        const int64_t d = lab - static_cast<int64_t>(col);
-        if (d >= 0 && d < 8) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (d == i) f[i] += g;
-        }
-        out.x = pack_bf16x2(f[0], f[1]);
-        out.y = pack_bf16x2(f[2], f[3]);
-        out.z = pack_bf16x2(f[4], f[5]);
-        out.w = pack_bf16x2(f[6], f[7]);
+      for (int i = 0; i < 4; ++i) {
+        f[2 * i] = __uint_as_float(w[i] << 16);
+        f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
       }
-      *vecp = out;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float e = f[i];
+        f[i] = (e > 0.f) ? e * fmaf(-b, __log2f(e), a) : 0.f;  // e == 0: p = 0, no contribution (and no 0 * inf)
+      }
+      const int64_t d = s_lab[ri] - static_cast<int64_t>(vb * 64 + (q & 7) * 8);
+      if (d >= 0 && d < 8) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (d == i) f[i] += g;
+      }
+      out.x = pack_bf16x2(f[0], f[1]);
+      out.y = pack_bf16x2(f[2], f[3]);
+      out.z = pack_bf16x2(f[4], f[5]);
+      out.w = pack_bf16x2(f[6], f[7]);
     }
+    return out;
+  };
+  const uint32_t q0 = threadIdx.x, q1 = threadIdx.x + 256;
+  uint32_t vb = vb0;
+  for (; vb + 1 < vb1; vb += 2) {
+    uint4* b0 = base + static_cast<size_t>(vb) * 512;
+    uint4* b1 = b0 + 512;
+    const uint4 a0 = b0[q0], a1 = b0[q1], a2 = b1[q0], a3 = b1[q1];
+    b0[q0] = transform(vb, q0, a0);
+    b0[q1] = transform(vb, q1, a1);
+    b1[q0] = transform(vb + 1, q0, a2);
+    b1[q1] = transform(vb + 1, q1, a3);
+  }
+  if (vb < vb1) {
+    uint4* b0 = base + static_cast<size_t>(vb) * 512;
+    const uint4 a0 = b0[q0], a1 = b0[q1];
+    b0[q0] = transform(vb, q0, a0);
+    b0[q1] = transform(vb, q1, a1);
   }
 }
 
