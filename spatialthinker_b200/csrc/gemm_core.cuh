@@ -53,7 +53,29 @@ struct TileSched {
   // actually ran at inside a long pipeline can be read back (nullptr: off)
   unsigned long long* probe;
   uint32_t acc_lead;      // wide tile: K-blocks accumulator 0 runs ahead of accumulator 1 at the tile ends (0..kStages-1)
+  // Split-K tail (accumulating epilogues only; filled in by launch_gemm). The persistent groups walk `num_units` work
+  // units: the first `whole_tiles` are whole tiles; when the tile count is not a multiple of the group count, the
+  // remaining tiles - which would occupy a fraction of the machine for a full tile time - are cut along K into
+  // `split_slices` units of `split_kpb` K-blocks each, so the last round is short and (nearly) full.
+  uint32_t split_tail;    // request (caller): 1 = allowed
+  uint32_t num_units, whole_tiles, split_slices, split_kpb;
+  uint32_t max_progress;  // most K-blocks any one group loads (progress-window bookkeeping)
 };
+
+// work unit u -> (tile, K-block range)
+__device__ __forceinline__ void decode_unit(const TileSched& s, uint32_t u, uint32_t& tile, uint32_t& kb0, uint32_t& kb1) {
+  if (u < s.whole_tiles) {
+    tile = u;
+    kb0 = 0;
+    kb1 = s.k_blocks;
+  } else {
+    const uint32_t j = u - s.whole_tiles;
+    const uint32_t q = j / s.split_slices;
+    tile = s.whole_tiles + q;
+    kb0 = (j - q * s.split_slices) * s.split_kpb;
+    kb1 = min(kb0 + s.split_kpb, s.k_blocks);
+  }
+}
 
 // Progress window `round` (1-based) starts: announce it, then make sure every one of the `groups` producers has at least
 // STARTED the previous window. That bounds the skew between CTA groups to two windows without ever stalling a producer
@@ -207,7 +229,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const uint32_t num_tiles = sched.m_blocks * sched.n_blocks;
+  const uint32_t num_units = sched.num_units;
   const uint32_t first_tile = blockIdx.x / kCta;
   const uint32_t tile_step = gridDim.x / kCta;
 
@@ -218,16 +240,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       const bool do_sync = leader && sched.sync_period != 0 && sched.sync_ctr != nullptr;
       uint32_t progress = 0, rounds_done = 0;
       bool give_up = false;
-      for (uint32_t t = first_tile; t < num_tiles; t += tile_step) {
-        uint32_t m_blk, n_blk;
+      for (uint32_t u = first_tile; u < num_units; u += tile_step) {
+        uint32_t t, kb0, kb1, m_blk, n_blk;
+        decode_unit(sched, u, t, kb0, kb1);
         decode_tile(sched, t, m_blk, n_blk);
         const int32_t m0 = static_cast<int32_t>(m_blk * Cfg::kTileRows + rank * Cfg::kRowsPerCta);
         const int32_t n0 = static_cast<int32_t>(n_blk * BLOCK_N + rank * Cfg::kLoadN);
-        for (uint32_t kb = 0; kb < sched.k_blocks; ++kb, ++progress) {
+        for (uint32_t kb = kb0; kb < kb1; ++kb, ++progress) {
           if (do_sync && progress != 0 && progress % sched.sync_period == 0)
             progress_sync(sched.sync_ctr, ++rounds_done, tile_step, give_up);
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          if (kb == 0) GRPO_TR(10, (t - first_tile) / tile_step);
+          if (kb == kb0) GRPO_TR(10, (u - first_tile) / tile_step);
           const int32_t k0 = static_cast<int32_t>(kb * kBlockK);
           uint8_t* sa = smem_a + stage * Cfg::kABytes;
           uint8_t* sb = smem_b + stage * Cfg::kBBytes;
@@ -254,9 +277,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
-      if (do_sync) {  // groups with fewer tiles keep arriving so the others never wait on them
-        const uint32_t max_tiles = (num_tiles + tile_step - 1) / tile_step;
-        const uint32_t total = max_tiles * sched.k_blocks;
+      if (do_sync) {  // groups with less work keep arriving so the others never wait on them
+        const uint32_t total = sched.max_progress;
         const uint32_t rounds = total == 0 ? 0 : (total - 1) / sched.sync_period;
         for (; rounds_done < rounds; ++rounds_done) atomicAdd(sched.sync_ctr, 1u);
       }
@@ -268,9 +290,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       constexpr uint32_t a_lbo = kAMn ? kBlockK * 128 : 0, b_lbo = kBMn ? kBlockK * 128 : 0;
       constexpr uint32_t a_kstep = kAMn ? kUmmaK * 128 : kUmmaK * 2, b_kstep = kBMn ? kUmmaK * 128 : kUmmaK * 2;
       constexpr uint32_t a_sub = kBlockM * 128;  // 128 rows further on: 16 KB in either majorness (two 8 KB MN atoms)
-      uint32_t it = 0, base = 0;  // base: K-blocks issued before this tile (ring position of its K-block 0)
-      const uint32_t kblocks = sched.k_blocks;
-      for (uint32_t t = first_tile; t < num_tiles; t += tile_step, ++it, base += kblocks) {
+      uint32_t it = 0, base = 0;  // base: K-blocks issued before this unit (ring position of its first K-block)
+      uint32_t kblocks = 0;       // K-blocks of the current unit; `kb` below counts from the unit's first K-block
+      for (uint32_t u = first_tile; u < num_units; u += tile_step, ++it, base += kblocks) {
+        {
+          uint32_t t_, kb0_, kb1_;
+          decode_unit(sched, u, t_, kb0_, kb1_);
+          kblocks = kb1_ - kb0_;
+        }
         // accumulator slots: kSub == 1 alternates them tile by tile, kSub == 2 uses both for every tile
         const uint32_t slot0 = (kSub == 1) ? (it & 1) : 0u;
         const uint32_t ap = (kSub == 1) ? ((it >> 1) & 1) : (it & 1);
@@ -344,7 +371,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     const uint32_t ew = warp - kEpiWarp0;
     const uint32_t grp = ew >> 2, quad = ew & 3;  // warp (4 + ew) may touch TMEM lanes 32 * (ew % 4) .. +31
     uint32_t it = 0;
-    for (uint32_t t = first_tile; t < num_tiles; t += tile_step, ++it) {
+    for (uint32_t u = first_tile; u < num_units; u += tile_step, ++it) {
+      uint32_t t, kb0_, kb1_;
+      decode_unit(sched, u, t, kb0_, kb1_);
       const uint32_t slot = (kSub == 1) ? (it & 1) : grp;
       const uint32_t ap = (kSub == 1) ? ((it >> 1) & 1) : (it & 1);
       EpiCtx c;

@@ -201,6 +201,7 @@ struct Knobs {
   int st_hint = 3;     // bit 0: stash bulk stores evict-first, bit 1: dW bulk reduce-adds evict-first (else normal)
   int clk_probe = 0;   // 1: the GEMM kernels record clock64 / globaltimer at entry and exit (grpo_debug_probe_offset)
   int dw_tma = 1;      // dW GEMM epilogue: 1 = bulk tensor reduce-add from shared memory, 0 = per-thread red.global.add
+  int dw_split = 1;    // dW GEMM: split-K tail for the last, partial round of tiles (TileSched::split_tail)
 };
 static Knobs g_knobs;
 static std::once_flag g_knobs_once;
@@ -222,6 +223,7 @@ static void init_knobs() {
     g_knobs.wait_hint_ns = env_int("GRPO_WAIT_HINT_NS", g_knobs.wait_hint_ns);
     g_knobs.epi_mode = env_int("GRPO_EPI_MODE", g_knobs.epi_mode) & 7;
     g_knobs.dw_tma = env_int("GRPO_DW_TMA", g_knobs.dw_tma) != 0;
+    g_knobs.dw_split = env_int("GRPO_DW_SPLIT", g_knobs.dw_split) != 0;
     g_knobs.acc_lead = env_int("GRPO_ACC_LEAD", g_knobs.acc_lead);
     g_knobs.st_hint = env_int("GRPO_ST_HINT", g_knobs.st_hint) & 3;
   });
@@ -248,8 +250,10 @@ static int get_dev(DevInfo* out) {
 }
 
 // ------------------------------------------------------------------------------------------ GEMM launch
+static inline uint32_t cdiv(uint64_t a, uint64_t b) { return static_cast<uint32_t>((a + b - 1) / b); }
+
 template <int kCta, int kSub, int BLOCK_N, int kStages, int kAMode, bool kBMn, class Epi>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const TileSched& sched,
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, TileSched sched,
                        const typename Epi::Params& ep, int sms, cudaStream_t stream) {
   using Cfg = GemmCfg<kCta, kSub, BLOCK_N, kStages>;
   auto kern = gemm_kernel<kCta, kSub, BLOCK_N, kStages, kAMode, kBMn, Epi>;
@@ -259,6 +263,23 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const TileS
   if (tiles == 0) return 0;
   uint32_t groups = static_cast<uint32_t>(sms / kCta);
   if (groups > tiles) groups = tiles;
+  // work units: whole tiles, plus - for accumulating epilogues - a split-K tail when the last round of tiles would
+  // leave more than half of the groups idle for a full tile time
+  const uint32_t rem = tiles % groups;
+  sched.num_units = sched.whole_tiles = tiles;
+  sched.split_slices = sched.split_kpb = 0;
+  sched.max_progress = cdiv(tiles, groups) * sched.k_blocks;
+  if (sched.split_tail && rem != 0 && 2 * rem <= groups && sched.k_blocks >= 2) {
+    uint32_t slices = groups / rem;
+    if (slices > sched.k_blocks) slices = sched.k_blocks;
+    const uint32_t kpb = cdiv(sched.k_blocks, slices);
+    slices = cdiv(sched.k_blocks, kpb);  // every slice holds at least one K-block
+    sched.whole_tiles = tiles - rem;
+    sched.split_slices = slices;
+    sched.split_kpb = kpb;
+    sched.num_units = sched.whole_tiles + rem * slices;  // rem * slices <= groups: one more (short) round
+    sched.max_progress = (tiles / groups) * sched.k_blocks + kpb;
+  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(groups * kCta);
   cfg.blockDim = dim3(Cfg::kThreads);
@@ -281,8 +302,6 @@ constexpr int kBlockN = 256;
 constexpr int kStages11 = 4;  // 1 CTA,  128 + 256 rows = 48 KB
 constexpr int kStages21 = 6;  // pair,   128 + 128 rows = 32 KB
 constexpr int kStages22 = 4;  // pair,   256 + 128 rows = 48 KB   (wide tile)
-
-static inline uint32_t cdiv(uint64_t a, uint64_t b) { return static_cast<uint32_t>((a + b - 1) / b); }
 
 // Tile geometry for a knob setting: rows of A per CTA-group tile.
 static inline int tile_rows(int cta_group, int ksub) { return kBlockM * cta_group * (cta_group == 2 ? ksub : 1); }
@@ -509,6 +528,7 @@ static int chunk_backward(const DevInfo& dev, const Workspace& w, const __nv_bfl
     s.m_fast = 0;  // the H column blocks of one vocab block run together: the stash panel is read from HBM once
     s.sync_period = static_cast<uint32_t>(dev.sync_dw);
     s.sync_ctr = w.sync + 2;
+    s.split_tail = static_cast<uint32_t>(dev.dw_split);  // the epilogue accumulates (reduce-add): K slices just add up
     s.probe = dev.clk_probe ? w.probe + 2048 : nullptr;
     if (dev.l2_hints & 2) {  // the (scaled) hidden chunk is re-read for every vocab block; the stash streams through once
       s.hint_a = kEvictFirst;
@@ -572,6 +592,7 @@ int grpo_set_option(const char* name, int value) {
   else if (!strcmp(name, "st_hint")) g_knobs.st_hint = value & 3;
   else if (!strcmp(name, "clk_probe")) g_knobs.clk_probe = value != 0;
   else if (!strcmp(name, "acc_lead")) g_knobs.acc_lead = value < 0 ? 0 : value;
+  else if (!strcmp(name, "dw_split")) g_knobs.dw_split = value != 0;
   else if (!strcmp(name, "chunk_rows")) g_knobs.chunk_rows = value > 0 ? (value + 511) / 512 * 512 : 0;
   else return fail(GRPO_ERR_ARG, "unknown option '%s'", name);
   return 0;
@@ -1194,6 +1215,7 @@ int grpo_debug_gemm(const void* a, const void* b, float* c, int64_t m, int64_t n
   memcpy(&p2, &p1, sizeof(p1));
   TileSched s{};
   s.m_fast = 1;
+  s.split_tail = (accumulate != 0 && dev.dw_split != 0) ? 1u : 0u;
   // A: 0 = [m][k], 1 = [k][m], 2 = blocked [m/64][k/64][64][64], 3 = blocked [k/64][m/64][64 k][64 m]
   const uint64_t a_pitch = a_mn_major == 0 ? k : (a_mn_major == 1 ? m : (a_mn_major == 2 ? (k + 63) / 64 : (m + 63) / 64));
   const uint64_t b_pitch = b_mn_major ? n : k;

@@ -101,6 +101,45 @@ def test_debug_gemm_fp32_epilogues(st, dev, tma, accumulate):
     assert bool((c[m:] == 2.5).all())
 
 
+@pytest.mark.parametrize("cta,ksub_rows", [(2, 512), (1, 128)])
+@pytest.mark.parametrize("a_mode,b_mn", [(0, 0), (3, 1)])
+def test_debug_gemm_split_k_tail(st, dev, cta, ksub_rows, a_mode, b_mn):
+    """More tiles than persistent CTA groups with a small remainder: the last round is cut along K into slices that the
+    accumulating epilogue adds up (the dW GEMM's tail). Same result as without the split, and as fp64 torch."""
+    from spatialthinker_b200 import _lib
+
+    lib = _lib.load()
+    groups = 148 // cta
+    tiles_n = 3
+    tiles_m = (groups + 5 + tiles_n - 1) // tiles_n + 1  # a handful of tiles beyond one full round
+    m, n, k = tiles_m * ksub_rows - 37, tiles_n * 256 - 8, 64 * 23 + 40  # ragged in every dimension, 24 K-blocks
+    g = torch.Generator().manual_seed(17)
+    a = torch.randn(m, k, generator=g).to(torch.bfloat16)
+    b = torch.randn(n, k, generator=g).to(torch.bfloat16)
+    want = a.double() @ b.double().t() + 1.0
+    if a_mode == 3:  # blocked [k/64][m/64][64 k][64 m] image of A, as the dW GEMM reads the stash
+        kp, mp = (k + 63) // 64 * 64, (m + 63) // 64 * 64
+        pad = torch.zeros(mp, kp, dtype=torch.bfloat16)
+        pad[:m, :k] = a
+        a_d = pad.view(mp // 64, 64, kp // 64, 64).permute(2, 0, 3, 1).contiguous().to(dev)
+    else:
+        a_d = a.to(dev)
+    b_d = (b.t().contiguous() if b_mn else b).to(dev)
+    outs = []
+    for split in (1, 0):
+        c = torch.full((m, n), 1.0, device=dev)
+        _lib.check(lib.grpo_set_option(b"dw_split", split), "set_option")
+        try:
+            _lib.check(lib.grpo_debug_gemm(a_d.data_ptr(), b_d.data_ptr(), c.data_ptr(), m, n, k, a_mode, b_mn, cta, 1,
+                                           _lib.stream_ptr(dev)), "gemm")
+            torch.cuda.synchronize()
+        finally:
+            lib.grpo_set_option(b"dw_split", 1)
+        outs.append(c.cpu())
+    np.testing.assert_allclose(outs[0].double().numpy(), want.numpy(), rtol=0, atol=5e-3)
+    np.testing.assert_allclose(outs[0].numpy(), outs[1].numpy(), rtol=0, atol=2e-3)  # fp32 summation order differs
+
+
 def test_epilogue_variants_agree(st, dev):
     """Softmax-epilogue variants (plain loop / pipelined TMEM drain / stash through bulk tensor stores) and dW-epilogue
     variants must give the same log-probs bit for bit and the same gradients up to fp32 accumulation order."""
