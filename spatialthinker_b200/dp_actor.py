@@ -25,7 +25,7 @@ import torch
 import torch.distributed as dist
 
 from . import _lib
-from .fused import fused_lm_head_log_probs, grpo_micro_batch_step
+from .fused import compact_index, fused_lm_head_log_probs, gather_rows, grpo_micro_batch_step, scatter_rows
 from .sharding import allreduce_mean_
 
 __all__ = ["ActorConfig", "DataParallelPPOActor", "append_to_dict"]
@@ -132,12 +132,33 @@ class DataParallelPPOActor:
                                 if k in _get(data, "batch")]
         if self.hidden_fn is not None:  # whatever the body needs travels with the micro-batch
             keys = list(_get(data, "batch").keys())
+        if "response_mask" in _get(data, "batch") and "response_mask" not in keys:
+            keys.append("response_mask")
+        micro_batches = data.select(keys).split(self.config.micro_batch_size_per_device_for_experience)
+        # padded response slots are dropped before the GEMM when a mask travels with the batch (ONE device->host read of
+        # the per-micro-batch token counts; the reference computes log-probs for padding and masks them later). Padded
+        # slots then read 0 instead of the reference's don't-care values.
+        counts = None
+        if self.compact_padding and micro_batches and (
+                "response_mask" in micro_batches[0].batch or "attention_mask" in micro_batches[0].batch):
+            sums = [(self._response_mask({**mb.batch}) != 0).sum() for mb in micro_batches]
+            counts = torch.stack(sums).cpu().tolist()
         outs = []
-        for mb in data.select(keys).split(self.config.micro_batch_size_per_device_for_experience):
+        for i, mb in enumerate(micro_batches):
             micro = {**mb.batch, **mb.non_tensor_batch}
             hidden = self._hidden(micro, train=False)
-            logp, _ = fused_lm_head_log_probs(hidden, self.weight.detach(), micro["responses"], temperature)
-            outs.append(logp)
+            labels = micro["responses"]
+            valid = counts[i] if counts is not None else labels.numel()
+            if 0 < valid < labels.numel():
+                mask = self._response_mask(micro)
+                gather_idx, inverse, _ = compact_index(mask)
+                logp_valid, _ = fused_lm_head_log_probs(
+                    gather_rows(hidden.reshape(-1, hidden.shape[-1]), gather_idx, valid), self.weight.detach(),
+                    gather_rows(labels.reshape(-1), gather_idx, valid), temperature)
+                outs.append(scatter_rows(logp_valid, inverse).view(labels.shape))
+            else:
+                logp, _ = fused_lm_head_log_probs(hidden, self.weight.detach(), labels, temperature)
+                outs.append(logp)
         return torch.concat(outs, dim=0)
 
     def update_policy(self, data) -> Dict[str, Any]:

@@ -605,7 +605,12 @@ def test_update_policy_matches_reference_loop(st, dev):
     data = st.TensorBatch(tensors, meta_info={"temperature": 0.9})
     lp = actor.compute_log_prob(data)
     want_lp, _ = O.lm_head_log_probs(x["hidden"], x["weight"], x["labels"], 0.9)
-    assert lp.shape == (bsz, tl) and float((lp.cpu() - want_lp).abs().max()) < TOL_LOGP
+    valid = x["mask"].bool()
+    # padded slots are dropped before the GEMM (compact_padding, the default) and read 0; without it every slot is computed
+    assert lp.shape == (bsz, tl) and float((lp.cpu() - want_lp)[valid].abs().max()) < TOL_LOGP
+    assert float(lp.cpu()[~valid].abs().max()) == 0.0
+    full = st.DataParallelPPOActor(cfg, x["weight"].to(dev), compact_padding=False).compute_log_prob(data)
+    assert float((full.cpu() - want_lp).abs().max()) < TOL_LOGP
     dws = []
     orig_step = actor._optimizer_step
 
