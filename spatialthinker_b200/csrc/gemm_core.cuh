@@ -57,6 +57,11 @@ struct TileSched {
   // units: the first `whole_tiles` are whole tiles; when the tile count is not a multiple of the group count, the
   // remaining tiles - which would occupy a fraction of the machine for a full tile time - are cut along K into
   // `split_slices` units of `split_kpb` K-blocks each, so the last round is short and (nearly) full.
+  // Wide tile, epilogues that support it (Epi::kCanShare): both epilogue warpgroups drain accumulator 0 first (half of
+  // its columns each), then accumulator 1, instead of one warpgroup per accumulator. Accumulator 0 - which the MMA warp
+  // finishes `acc_lead` K-blocks early - is then free again after half the drain time, and the next tile's first MMAs
+  // overlap the drain of accumulator 1.
+  uint32_t epi_share;
   uint32_t split_tail;    // request (caller): 1 = allowed
   uint32_t num_units, whole_tiles, split_slices, split_kpb;
   uint32_t max_progress;  // most K-blocks any one group loads (progress-window bookkeeping)
@@ -140,6 +145,7 @@ struct EpiCtx {
   uint32_t tmem_acc;  // TMEM address of this warp's lanes, column 0 of the accumulator
   uint32_t epi_warp;  // index of this warp among the CTA's epilogue warps (its 4 KB staging buffer in smem_epi)
   uint32_t row0;      // first global output row of this warp (row - lane)
+  uint32_t part;      // index of this call's (column block, column part) among a row's partial results
 };
 constexpr int kEpiStageBytes = 4096;  // per-epilogue-warp staging buffer for shared -> global bulk stores
 
@@ -217,7 +223,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);                        // one tcgen05.commit
-      mbar_init(&tmem_empty[i], kCta * kNumEpiThreads);  // the warpgroup draining this slot, in every CTA of the pair
+      // the warpgroup(s) draining this slot, in every CTA of the pair
+      mbar_init(&tmem_empty[i], kCta * kNumEpiThreads * ((kSub == 2 && Epi::kCanShare && sched.epi_share) ? 2 : 1));
     }
     fence_mbar_init();
   }
@@ -374,6 +381,37 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     for (uint32_t u = first_tile; u < num_units; u += tile_step, ++it) {
       uint32_t t, kb0_, kb1_;
       decode_unit(sched, u, t, kb0_, kb1_);
+      if constexpr (kSub == 2 && Epi::kCanShare) {
+        if (sched.epi_share) {  // both warpgroups on accumulator 0, then both on accumulator 1; `grp` picks the columns
+          uint32_t m_blk, n_blk;
+          decode_tile(sched, t, m_blk, n_blk);
+#pragma unroll 1
+          for (uint32_t slot = 0; slot < 2; ++slot) {
+            EpiCtx c;
+            c.n_blk = n_blk;
+            c.part = n_blk * 2 + grp;
+            c.warp = quad;
+            c.lane = lane;
+            c.epi_warp = ew;
+            c.row0 = m_blk * Cfg::kTileRows + rank * Cfg::kRowsPerCta + slot * kBlockM + quad * 32;
+            c.row = c.row0 + lane;
+            c.col0 = n_blk * BLOCK_N + grp * (BLOCK_N / 2);
+            c.tmem_acc = tmem_base + slot * BLOCK_N + grp * (BLOCK_N / 2) + ((quad * 32u) << 16);
+            mbar_wait(&tmem_full[slot], it & 1, sched.wait_hint_ns);
+            tc_fence_after();
+            if (ew == 0 && lane == 0) GRPO_TR(4 + slot, it);
+            auto release = [&]() {
+              tc_fence_before();
+              if (leader) mbar_arrive(&tmem_empty[slot]);
+              else mbar_arrive_cluster(&tmem_empty[slot], 0);
+              if (ew == 0 && lane == 0) GRPO_TR(6 + slot, it);
+            };
+            Epi::template run_cols<BLOCK_N / 2>(ep, c, smem_epi, release);
+            if (ew == 0 && lane == 0) GRPO_TR(8 + slot, it);
+          }
+          continue;
+        }
+      }
       const uint32_t slot = (kSub == 1) ? (it & 1) : grp;
       const uint32_t ap = (kSub == 1) ? ((it >> 1) & 1) : (it & 1);
       EpiCtx c;
@@ -386,6 +424,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       c.row = c.row0 + lane;
       c.col0 = c.n_blk * BLOCK_N;
       c.tmem_acc = tmem_base + slot * BLOCK_N + ((quad * 32u) << 16);
+      c.part = c.n_blk;
       mbar_wait(&tmem_full[slot], ap, sched.wait_hint_ns);
       tc_fence_after();
       if (quad == 0 && lane == 0) GRPO_TR(4 + (slot & 1), it);
@@ -438,6 +477,7 @@ struct EpiF32 {
     uint64_t policy;  // L2 eviction priority of the bulk reduce-add (kEvictNormal / kEvictFirst)
   };
   static constexpr int kSmemBytes = 8 * kEpiStageBytes;
+  static constexpr bool kCanShare = false;
   __device__ static void finish(const Params& p, uint32_t lane) {
     if (p.use_tma && lane == 0) bulk_wait_all();
   }
@@ -520,6 +560,7 @@ struct EpiBF16 {
     int64_t ld_gather;
   };
   static constexpr int kSmemBytes = 0;
+  static constexpr bool kCanShare = false;
   __device__ static void finish(const Params&, uint32_t) {}
   template <class Release>
   __device__ static void run(const Params& p, const EpiCtx& c, uint8_t*, Release&& release) {

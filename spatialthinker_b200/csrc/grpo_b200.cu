@@ -202,6 +202,7 @@ struct Knobs {
   int clk_probe = 0;   // 1: the GEMM kernels record clock64 / globaltimer at entry and exit (grpo_debug_probe_offset)
   int dw_tma = 1;      // dW GEMM epilogue: 1 = bulk tensor reduce-add from shared memory, 0 = per-thread red.global.add
   int dw_split = 1;    // dW GEMM: split-K tail for the last, partial round of tiles (TileSched::split_tail)
+  int epi_share = 0;   // logits GEMM, wide tile: both epilogue warpgroups drain accumulator 0, then 1 (TileSched::epi_share)
 };
 static Knobs g_knobs;
 static std::once_flag g_knobs_once;
@@ -224,6 +225,7 @@ static void init_knobs() {
     g_knobs.epi_mode = env_int("GRPO_EPI_MODE", g_knobs.epi_mode) & 7;
     g_knobs.dw_tma = env_int("GRPO_DW_TMA", g_knobs.dw_tma) != 0;
     g_knobs.dw_split = env_int("GRPO_DW_SPLIT", g_knobs.dw_split) != 0;
+    g_knobs.epi_share = env_int("GRPO_EPI_SHARE", g_knobs.epi_share) != 0;
     g_knobs.acc_lead = env_int("GRPO_ACC_LEAD", g_knobs.acc_lead);
     g_knobs.st_hint = env_int("GRPO_ST_HINT", g_knobs.st_hint) & 3;
   });
@@ -374,7 +376,7 @@ static Workspace carve(void* base, int64_t rows, int64_t hdim, int64_t vocab, bo
     w.stash = reinterpret_cast<__nv_bfloat16*>(take(static_cast<size_t>(w.rows_pad) * w.stash_vb * 64 * 2));
     w.hd_scaled = reinterpret_cast<__nv_bfloat16*>(take(static_cast<size_t>(w.chunk_rows) * hdim * 2));
   }
-  const size_t part = static_cast<size_t>(w.n_tiles) * w.rows_pad * 4;
+  const size_t part = 2 * static_cast<size_t>(w.n_tiles) * w.rows_pad * 4;  // two column parts per tile when epi_share
   w.part_sum = reinterpret_cast<float*>(take(part));
   w.part_ez = reinterpret_cast<float*>(take(part));
   const size_t vec = static_cast<size_t>(w.rows_pad) * 4;
@@ -451,6 +453,8 @@ static int chunk_forward(const DevInfo& dev, const Workspace& w, const __nv_bflo
   }
   s.sync_period = static_cast<uint32_t>(dev.sync_fwd);
   s.sync_ctr = w.sync;
+  const bool share = dev.epi_share != 0 && dev.cta_group == 2 && dev.ksub == 2;  // wide tile only
+  s.epi_share = share ? 1u : 0u;
   s.probe = dev.clk_probe ? w.probe : nullptr;
   if (dev.l2_hints & 1) {  // the hidden panel is re-read under every vocab tile; a W tile is dead after one panel pass
     s.hint_a = kEvictLast;
@@ -465,8 +469,8 @@ static int chunk_forward(const DevInfo& dev, const Workspace& w, const __nv_bflo
   PhaseScope ps(PH_ROW_STATS, stream);
   combine_rows_kernel<<<cdiv(n, 32), dim3(32, 8), 0, stream>>>(
       w.part_sum, want_entropy ? w.part_ez : nullptr, w.a_label, labels + r0, static_cast<uint32_t>(n),
-      static_cast<uint32_t>(w.rows_pad), static_cast<uint32_t>(w.n_tiles), static_cast<uint32_t>(v), 1.f / temperature,
-      lse_out, logp_out, ent_out, w.inv_sum);
+      static_cast<uint32_t>(w.rows_pad), static_cast<uint32_t>(w.n_tiles * (share ? 2 : 1)), static_cast<uint32_t>(v),
+      1.f / temperature, lse_out, logp_out, ent_out, w.inv_sum);
   count_launch();
   GRPO_CUDA(cudaGetLastError());
   return 0;
@@ -593,6 +597,7 @@ int grpo_set_option(const char* name, int value) {
   else if (!strcmp(name, "clk_probe")) g_knobs.clk_probe = value != 0;
   else if (!strcmp(name, "acc_lead")) g_knobs.acc_lead = value < 0 ? 0 : value;
   else if (!strcmp(name, "dw_split")) g_knobs.dw_split = value != 0;
+  else if (!strcmp(name, "epi_share")) g_knobs.epi_share = value != 0;
   else if (!strcmp(name, "chunk_rows")) g_knobs.chunk_rows = value > 0 ? (value + 511) / 512 * 512 : 0;
   else return fail(GRPO_ERR_ARG, "unknown option '%s'", name);
   return 0;

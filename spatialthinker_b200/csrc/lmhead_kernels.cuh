@@ -74,6 +74,7 @@ struct EpiSoftmax {
     uint64_t policy;  // L2 eviction priority of the stash stores: it is next read by another kernel, after 5.8 GB went by
   };
   static constexpr int kSmemBytes = 8 * kEpiStageBytes;
+  static constexpr bool kCanShare = true;  // a call can cover BLOCK_N / 2 columns of an accumulator (TileSched::epi_share)
   __device__ static void finish(const Params& p, uint32_t lane) {
     if ((p.mode & 2) && lane == 0) bulk_wait_all();
   }
@@ -110,7 +111,7 @@ struct EpiSoftmax {
     }
   }
 
-  template <bool kWantEz, class Release>
+  template <bool kWantEz, int kCols, class Release>
   __device__ static __forceinline__ void run_full(const Params& p, const EpiCtx& c, uint8_t* smem_epi, Release&& release,
                                                   float c1, float off, __nv_bfloat16* srow, float& s0, float& s1,
                                                   float& t0, float& t1) {
@@ -122,10 +123,10 @@ struct EpiSoftmax {
     const int32_t rb = static_cast<int32_t>(c.row0 >> 6), r_in = static_cast<int32_t>(c.row0 & 63);
     const int32_t vb0 = static_cast<int32_t>(c.col0 >> 6);
     uint32_t va[32], vb[32];
-    static_assert((BLOCK_N / 32) % 2 == 0, "column groups are drained in pairs (one 64-column stash block)");
+    static_assert((kCols / 32) % 2 == 0, "column groups are drained in pairs (one 64-column stash block)");
     tmem_ld_32x32(c.tmem_acc, va);
 #pragma unroll 1
-    for (int g = 0; g < BLOCK_N / 32; g += 2) {
+    for (int g = 0; g < kCols / 32; g += 2) {
       tmem_ld_wait();
       tmem_ld_32x32(c.tmem_acc + (g + 1) * 32, vb);
       if (via_tma) {  // the previous 64-column block must have left the staging buffer
@@ -135,7 +136,7 @@ struct EpiSoftmax {
       __nv_bfloat16* gdst = srow + (g >> 1) * 4096;
       group_full<kWantEz>(va, c1, off, s0, s1, t0, t1, want_stash, smem_row, sw, 0, gdst);
       tmem_ld_wait();
-      if (g + 2 < BLOCK_N / 32) tmem_ld_32x32(c.tmem_acc + (g + 2) * 32, va);
+      if (g + 2 < kCols / 32) tmem_ld_32x32(c.tmem_acc + (g + 2) * 32, va);
       else release();  // last TMEM read of this accumulator has landed
       group_full<kWantEz>(vb, c1, off, s0, s1, t0, t1, want_stash, smem_row, sw, 4, gdst + 32);
       if (via_tma) {
@@ -180,7 +181,7 @@ struct EpiSoftmax {
   }
 
   // mode bits 0-2: pipelined TMEM drain, one bulk store per 32-column group out of alternating 2 KB staging halves
-  template <bool kWantEz, class Release>
+  template <bool kWantEz, int kCols, class Release>
   __device__ static __forceinline__ void run_half(const Params& p, const EpiCtx& c, uint8_t* smem_epi, Release&& release,
                                                   float c1, float off, float& s0, float& s1, float& t0, float& t1) {
     uint8_t* buf = smem_epi + c.epi_warp * kEpiStageBytes;
@@ -211,12 +212,12 @@ struct EpiSoftmax {
     };
     tmem_ld_32x32(c.tmem_acc, va);
 #pragma unroll 1
-    for (int g = 0; g < BLOCK_N / 32; g += 2) {
+    for (int g = 0; g < kCols / 32; g += 2) {
       tmem_ld_wait();
       tmem_ld_32x32(c.tmem_acc + (g + 1) * 32, vb);
       emit(va, g);
       tmem_ld_wait();
-      if (g + 2 < BLOCK_N / 32) tmem_ld_32x32(c.tmem_acc + (g + 2) * 32, va);
+      if (g + 2 < kCols / 32) tmem_ld_32x32(c.tmem_acc + (g + 2) * 32, va);
       else release();  // last TMEM read of this accumulator has landed
       emit(vb, g + 1);
     }
@@ -224,9 +225,15 @@ struct EpiSoftmax {
 
   template <class Release>
   __device__ static void run(const Params& p, const EpiCtx& c, uint8_t* smem_epi, Release&& release) {
+    run_cols<BLOCK_N>(p, c, smem_epi, release);
+  }
+
+  // kCols columns of the accumulator starting at global column c.col0 / TMEM address c.tmem_acc
+  template <int kCols, class Release>
+  __device__ static void run_cols(const Params& p, const EpiCtx& c, uint8_t* smem_epi, Release&& release) {
     const uint32_t row = c.row, col0 = c.col0;
     const bool row_ok = row < p.rows;
-    const uint32_t ncols = min(static_cast<uint32_t>(BLOCK_N), p.vocab - col0);
+    const uint32_t ncols = col0 < p.vocab ? min(static_cast<uint32_t>(kCols), p.vocab - col0) : 0u;
     const uint32_t ngroups = (ncols + 31) >> 5;  // column groups of 32 that hold at least one real vocabulary entry
     const float c1 = p.scale * kLog2e;
     // rows past the last token get an infinite offset: every exponential is then exactly 0 (zeros in the stash) with no
@@ -239,16 +246,19 @@ struct EpiSoftmax {
     __nv_bfloat16* srow = want_stash
         ? p.stash + (static_cast<size_t>(row >> 6) * p.stash_vb + (col0 >> 6)) * 4096 + (row & 63) * 64
         : nullptr;
-    const uint32_t store_groups = want_stash ? min(static_cast<uint32_t>(BLOCK_N / 32), 2 * (p.stash_vb - (col0 >> 6))) : 0;
+    const uint32_t vb_here = col0 >> 6;  // first 64-column stash block of this call (may lie past the stash's last block)
+    const uint32_t store_groups =
+        (want_stash && vb_here < p.stash_vb) ? min(static_cast<uint32_t>(kCols / 32), 2 * (p.stash_vb - vb_here)) : 0;
 
     float s0 = 0.f, s1 = 0.f, t0 = 0.f, t1 = 0.f;
-    if ((p.mode & 7) == 7 && want_stash && ncols == BLOCK_N) {
-      if (want_ez) run_half<true>(p, c, smem_epi, release, c1, off, s0, s1, t0, t1);
-      else run_half<false>(p, c, smem_epi, release, c1, off, s0, s1, t0, t1);
-    } else if ((p.mode & 1) && ncols == BLOCK_N) {  // every tile but the last one of the vocabulary
-      if (want_ez) run_full<true>(p, c, smem_epi, release, c1, off, srow, s0, s1, t0, t1);
-      else run_full<false>(p, c, smem_epi, release, c1, off, srow, s0, s1, t0, t1);
+    if ((p.mode & 7) == 7 && want_stash && ncols == kCols) {
+      if (want_ez) run_half<true, kCols>(p, c, smem_epi, release, c1, off, s0, s1, t0, t1);
+      else run_half<false, kCols>(p, c, smem_epi, release, c1, off, s0, s1, t0, t1);
+    } else if ((p.mode & 1) && ncols == kCols) {  // every tile but the last one of the vocabulary
+      if (want_ez) run_full<true, kCols>(p, c, smem_epi, release, c1, off, srow, s0, s1, t0, t1);
+      else run_full<false, kCols>(p, c, smem_epi, release, c1, off, srow, s0, s1, t0, t1);
     } else {
+      if (ngroups == 0) release();  // nothing to read: columns wholly past the vocabulary
 #pragma unroll 1
       for (uint32_t g = 0; g < ngroups; ++g) {
         uint32_t v[32];
@@ -298,7 +308,7 @@ struct EpiSoftmax {
       }
     }
     if (row_ok) {
-      const size_t o = static_cast<size_t>(c.n_blk) * p.rows_pad + row;
+      const size_t o = static_cast<size_t>(c.part) * p.rows_pad + row;
       p.part_sum[o] = s0 + s1;
       if (want_ez) p.part_ez[o] = (t0 + t1) * p.scale;
     }
