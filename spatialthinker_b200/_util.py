@@ -31,7 +31,11 @@ def require_cuda(*tensors: torch.Tensor) -> torch.device:
 
 
 def scratch(kind: str, device: torch.device, nbytes: int) -> torch.Tensor:
-    """A cached, grow-only byte buffer per (kind, device): kernel workspaces are reused across calls."""
+    """A cached, grow-only byte buffer per (kind, device): kernel workspaces are reused across calls.
+
+    The buffer is shared by every call on that device, so calls must be ordered on ONE stream (the actor loop's: the
+    library only enqueues on torch's current stream). Code that drives the head from several streams at once must hand
+    each stream its own workspace through the C ABI (``grpo_*_workspace_bytes``) instead of this cache."""
     key = (kind, device.index if device.index is not None else torch.cuda.current_device())
     buf = _scratch.get(key)
     if buf is None or buf.numel() < nbytes:
