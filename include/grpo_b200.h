@@ -62,7 +62,9 @@ const char* grpo_last_error(void);
 #define GRPO_NUM_PHASES 6
 long long grpo_launch_count(void);
 /* Tuning knobs for experiments (process-wide): "cta_group" 1|2, "fwd_panel" row blocks, "sync_fwd" / "sync_dh" /
- * "sync_dw" progress-barrier periods in K-blocks (0 = off), "l2_hints" 0|1. Defaults are the measured configuration. */
+ * "sync_dw" progress-barrier periods in K-blocks (0 = off), "l2_hints" 0|1, "dw_split" 0|1|2 (split-K tail of the dW GEMM;
+ * 2 = the multi-round plan), "dh_split" 0|1 (dHidden GEMM: fp32 split-K path when its tiles are not a whole number of
+ * rounds). Defaults are the measured configuration. */
 int grpo_set_option(const char* name, int value);
 /* Measurement aid: with option "clk_probe" = 1 the three GEMM kernels of the chunk pipeline write
  * 1024 x uint64 each (order logits / dHidden / dW) at this byte offset of the caller's workspace:
@@ -240,6 +242,14 @@ int grpo_logprob_from_logits_bwd(const void* logits, int logits_dtype, const int
  * ------------------------------------------------------------------------------------------------------------------ */
 int grpo_debug_gemm(const void* a, const void* b, float* c, int64_t m, int64_t n, int64_t k, int a_mn_major,
                     int b_mn_major, int cta_group, int accumulate, grpo_stream_t stream);
+
+/* Debug / test entry (host only, no device work): the work-unit plan a persistent GEMM launch would use for `tiles`
+ * output tiles of `k_blocks` K-blocks on `groups_avail` CTA groups. split_mode: 0 = whole tiles, 1 = one short split-K
+ * round for a small remainder (dW GEMM), 2 = best slice count over several short rounds (dHidden GEMM, fp32 split path).
+ *   units (nullable) int32 [max_units][3] = {tile, first K-block, end K-block} per unit, in walk order (unit u runs on
+ *   group u % groups);  info (nullable) int32 [4] = {groups launched, units, progress-window bound, slices per tile}. */
+int grpo_debug_plan_units(int64_t tiles, int64_t k_blocks, int groups_avail, int split_mode, int32_t* units,
+                          int64_t max_units, int32_t* info);
 
 #ifdef __cplusplus
 }

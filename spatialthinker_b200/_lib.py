@@ -68,6 +68,7 @@ _SIGNATURES = {
     "grpo_logprob_from_logits": (c_int, [_P, c_int, _P, c_int64, c_int64, c_int64, _P, _P, _P, _P]),
     "grpo_logprob_from_logits_bwd": (c_int, [_P, c_int, _P, _P, _P, _P, _P, c_int64, c_int64, c_int64, _P, c_int64, _P]),
     "grpo_debug_gemm": (c_int, [_P, _P, _P, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_int, _P]),
+    "grpo_debug_plan_units": (c_int, [c_int64, c_int64, c_int, c_int, _P, c_int64, _P]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

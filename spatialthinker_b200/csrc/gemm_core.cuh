@@ -62,23 +62,34 @@ struct TileSched {
   // finishes `acc_lead` K-blocks early - is then free again after half the drain time, and the next tile's first MMAs
   // overlap the drain of accumulator 1.
   uint32_t epi_share;
-  uint32_t split_tail;    // request (caller): 1 = allowed
+  uint32_t split_tail;    // request (caller): 0 = off, 1 = one short extra round (dW GEMM), 2 = best slice count over
+                          // several short rounds, slice-major (dHidden GEMM on its fp32 split path)
   uint32_t num_units, whole_tiles, split_slices, split_kpb;
+  uint32_t split_tiles;   // 0: tail units are ordered tile-major (all slices of a tile are neighbours); otherwise the
+                          // number of tail tiles, and the units are ordered slice-major: the groups that run side by
+                          // side work on the SAME K range of neighbouring tiles, so the operand panels those tiles share
+                          // are fetched from HBM once, as in the whole-tile rounds
   uint32_t max_progress;  // most K-blocks any one group loads (progress-window bookkeeping)
 };
 
 // work unit u -> (tile, K-block range)
-__device__ __forceinline__ void decode_unit(const TileSched& s, uint32_t u, uint32_t& tile, uint32_t& kb0, uint32_t& kb1) {
+__host__ __device__ __forceinline__ void decode_unit(const TileSched& s, uint32_t u, uint32_t& tile, uint32_t& kb0, uint32_t& kb1) {
   if (u < s.whole_tiles) {
     tile = u;
     kb0 = 0;
     kb1 = s.k_blocks;
   } else {
     const uint32_t j = u - s.whole_tiles;
-    const uint32_t q = j / s.split_slices;
-    tile = s.whole_tiles + q;
-    kb0 = (j - q * s.split_slices) * s.split_kpb;
-    kb1 = min(kb0 + s.split_kpb, s.k_blocks);
+    if (s.split_tiles != 0) {  // slice-major
+      const uint32_t sl = j / s.split_tiles;
+      tile = s.whole_tiles + (j - sl * s.split_tiles);
+      kb0 = sl * s.split_kpb;
+    } else {
+      const uint32_t q = j / s.split_slices;
+      tile = s.whole_tiles + q;
+      kb0 = (j - q * s.split_slices) * s.split_kpb;
+    }
+    kb1 = (kb0 + s.split_kpb < s.k_blocks) ? kb0 + s.split_kpb : s.k_blocks;
   }
 }
 

@@ -203,6 +203,11 @@ struct Knobs {
   int dw_tma = 1;      // dW GEMM epilogue: 1 = bulk tensor reduce-add from shared memory, 0 = per-thread red.global.add
   int dw_split = 1;    // dW GEMM: split-K tail for the last, partial round of tiles (TileSched::split_tail)
   int epi_share = 0;   // logits GEMM, wide tile: both epilogue warpgroups drain accumulator 0, then 1 (TileSched::epi_share)
+  // dHidden GEMM: when its tile count is not a whole number of rounds over the CTA pairs (micro-batches that are not a
+  // multiple of 37 row tiles, e.g. the reference's 4-sequence micro-batches), accumulate in fp32 with a split-K tail and
+  // convert in a fix-up pass (chunk_backward). 0: always the direct bf16 epilogue. Measured on B200
+  // (profiles/r1_ab_dh_split.log): dHidden GEMM 3.93 -> 3.16 ms at 4096 rows, 1.68 -> 0.76 ms at 1024 rows.
+  int dh_split = 1;
 };
 static Knobs g_knobs;
 static std::once_flag g_knobs_once;
@@ -226,6 +231,7 @@ static void init_knobs() {
     g_knobs.dw_tma = env_int("GRPO_DW_TMA", g_knobs.dw_tma) != 0;
     g_knobs.dw_split = env_int("GRPO_DW_SPLIT", g_knobs.dw_split) != 0;
     g_knobs.epi_share = env_int("GRPO_EPI_SHARE", g_knobs.epi_share) != 0;
+    g_knobs.dh_split = env_int("GRPO_DH_SPLIT", g_knobs.dh_split) != 0;
     g_knobs.acc_lead = env_int("GRPO_ACC_LEAD", g_knobs.acc_lead);
     g_knobs.st_hint = env_int("GRPO_ST_HINT", g_knobs.st_hint) & 3;
   });
@@ -254,24 +260,60 @@ static int get_dev(DevInfo* out) {
 // ------------------------------------------------------------------------------------------ GEMM launch
 static inline uint32_t cdiv(uint64_t a, uint64_t b) { return static_cast<uint32_t>((a + b - 1) / b); }
 
-template <int kCta, int kSub, int BLOCK_N, int kStages, int kAMode, bool kBMn, class Epi>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, TileSched sched,
-                       const typename Epi::Params& ep, int sms, cudaStream_t stream) {
-  using Cfg = GemmCfg<kCta, kSub, BLOCK_N, kStages>;
-  auto kern = gemm_kernel<kCta, kSub, BLOCK_N, kStages, kAMode, kBMn, Epi>;
-  const size_t smem = Cfg::smem_bytes(Epi::kSmemBytes);
-  GRPO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  const uint32_t tiles = sched.m_blocks * sched.n_blocks;
-  if (tiles == 0) return 0;
-  uint32_t groups = static_cast<uint32_t>(sms / kCta);
-  if (groups > tiles) groups = tiles;
-  // work units: whole tiles, plus - for accumulating epilogues - a split-K tail when the last round of tiles would
-  // leave more than half of the groups idle for a full tile time
+// Split-K plan for a partial round of `rem` tiles on `groups` persistent CTA groups (TileSched::split_tail == 2): every
+// tail tile is cut along K into `slices` units and the rem * slices units are walked slice-major in `rounds` short
+// rounds. Picks the slice count (<= 16) with the least rounds x (slice length + one accumulator drain), in K-blocks.
+constexpr uint32_t kSplitDrainKb = 8;  // fp32 reduce-add drain of one wide tile ~ 8.4 k cycles ~ 8 K-blocks (r1_tile_trace.log)
+struct TailPlan {
+  uint32_t slices, kpb, rounds;
+  uint64_t cost;  // K-block times
+};
+static TailPlan plan_tail(uint32_t rem, uint32_t groups, uint32_t k_blocks) {
+  TailPlan best{1, k_blocks, (rem + groups - 1) / groups, 0};
+  best.cost = static_cast<uint64_t>(best.rounds) * (k_blocks + kSplitDrainKb);
+  for (uint32_t want = 2; want <= 16 && want <= k_blocks; ++want) {
+    const uint32_t kpb = (k_blocks + want - 1) / want;
+    const uint32_t slices = (k_blocks + kpb - 1) / kpb;  // every slice holds at least one K-block
+    const uint32_t rounds = static_cast<uint32_t>((static_cast<uint64_t>(rem) * slices + groups - 1) / groups);
+    const uint64_t cost = static_cast<uint64_t>(rounds) * (kpb + kSplitDrainKb);
+    if (cost < best.cost) best = TailPlan{slices, kpb, rounds, cost};
+  }
+  return best;
+}
+// Estimated duration (K-block times) of a GEMM of `tiles` tiles x `k_blocks` on `groups` groups: whole-tile rounds
+// only, or whole rounds + the planned split-K tail through the accumulating fp32 epilogue.
+static uint64_t gemm_cost_plain(uint32_t tiles, uint32_t groups, uint32_t k_blocks) {
+  return static_cast<uint64_t>((tiles + groups - 1) / groups) * k_blocks;
+}
+static uint64_t gemm_cost_split(uint32_t tiles, uint32_t groups, uint32_t k_blocks) {
+  const uint32_t rem = tiles % groups;
+  uint64_t c = static_cast<uint64_t>(tiles / groups) * (k_blocks + kSplitDrainKb);
+  if (rem != 0) c += plan_tail(rem, groups, k_blocks).cost;
+  return c;
+}
+
+// Work units of one launch: fills the unit fields of `sched` for `tiles` output tiles on at most `groups_avail`
+// persistent CTA groups and returns the number of groups to launch. Units are whole tiles, plus - for accumulating
+// epilogues (sched.split_tail != 0) - K slices of the tiles of the last, partial round.
+static uint32_t plan_units(TileSched& sched, uint32_t tiles, uint32_t groups_avail) {
+  uint32_t groups = groups_avail;
+  TailPlan plan{1, 0, 0, 0};
+  if (sched.split_tail == 2 && tiles % groups != 0 && sched.k_blocks >= 2)
+    plan = plan_tail(tiles % groups, groups, sched.k_blocks);  // may use every group even when tiles < groups
+  if (plan.slices <= 1 && groups > tiles) groups = tiles;
   const uint32_t rem = tiles % groups;
   sched.num_units = sched.whole_tiles = tiles;
-  sched.split_slices = sched.split_kpb = 0;
+  sched.split_slices = sched.split_kpb = sched.split_tiles = 0;
   sched.max_progress = cdiv(tiles, groups) * sched.k_blocks;
-  if (sched.split_tail && rem != 0 && 2 * rem <= groups && sched.k_blocks >= 2) {
+  if (plan.slices > 1) {  // mode 2: several short rounds of K slices, slice-major
+    sched.whole_tiles = tiles - rem;
+    sched.split_slices = plan.slices;
+    sched.split_kpb = plan.kpb;
+    sched.split_tiles = rem;
+    sched.num_units = sched.whole_tiles + rem * plan.slices;
+    sched.max_progress = (tiles / groups) * sched.k_blocks + plan.rounds * plan.kpb;
+  } else if (sched.split_tail == 1 && rem != 0 && 2 * rem <= groups && sched.k_blocks >= 2) {
+    // mode 1: the last round would leave more than half of the groups idle for a full tile time - one short round instead
     uint32_t slices = groups / rem;
     if (slices > sched.k_blocks) slices = sched.k_blocks;
     const uint32_t kpb = cdiv(sched.k_blocks, slices);
@@ -282,6 +324,20 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, TileSched s
     sched.num_units = sched.whole_tiles + rem * slices;  // rem * slices <= groups: one more (short) round
     sched.max_progress = (tiles / groups) * sched.k_blocks + kpb;
   }
+  return groups;
+}
+
+template <int kCta, int kSub, int BLOCK_N, int kStages, int kAMode, bool kBMn, class Epi>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, TileSched sched,
+                       const typename Epi::Params& ep, int sms, cudaStream_t stream) {
+  using Cfg = GemmCfg<kCta, kSub, BLOCK_N, kStages>;
+  auto kern = gemm_kernel<kCta, kSub, BLOCK_N, kStages, kAMode, kBMn, Epi>;
+  const size_t smem = Cfg::smem_bytes(Epi::kSmemBytes);
+  GRPO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  const uint32_t tiles = sched.m_blocks * sched.n_blocks;
+  if (tiles == 0) return 0;
+  if (sms / kCta <= 0) return fail(GRPO_ERR_ARG, "no CTA groups on this device");
+  const uint32_t groups = plan_units(sched, tiles, static_cast<uint32_t>(sms / kCta));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(groups * kCta);
   cfg.blockDim = dim3(Cfg::kThreads);
@@ -345,6 +401,7 @@ struct Workspace {
   // stream it from HBM in whole DRAM pages instead of 128-byte pieces 300 KB apart.
   __nv_bfloat16* stash = nullptr;
   __nv_bfloat16* hd_scaled = nullptr;  // [chunk_rows][H] row-scaled hidden: B operand of the dW GEMM
+  float* dh_acc = nullptr;             // [chunk_rows][H] fp32 accumulator of the dHidden GEMM's split-K path
   float *part_sum = nullptr, *part_ez = nullptr;  // [n_tiles][rows_pad]
   float *a_label = nullptr, *lse = nullptr, *inv_sum = nullptr, *dlogp = nullptr, *dent = nullptr, *ent = nullptr;
   float *row_scale = nullptr, *onehot = nullptr;
@@ -375,6 +432,7 @@ static Workspace carve(void* base, int64_t rows, int64_t hdim, int64_t vocab, bo
   if (with_stash) {
     w.stash = reinterpret_cast<__nv_bfloat16*>(take(static_cast<size_t>(w.rows_pad) * w.stash_vb * 64 * 2));
     w.hd_scaled = reinterpret_cast<__nv_bfloat16*>(take(static_cast<size_t>(w.chunk_rows) * hdim * 2));
+    w.dh_acc = reinterpret_cast<float*>(take(static_cast<size_t>(w.chunk_rows) * hdim * 4));
   }
   const size_t part = 2 * static_cast<size_t>(w.n_tiles) * w.rows_pad * 4;  // two column parts per tile when epi_share
   w.part_sum = reinterpret_cast<float*>(take(part));
@@ -499,7 +557,46 @@ static int chunk_backward(const DevInfo& dev, const Workspace& w, const __nv_bfl
     count_launch();
     GRPO_CUDA(cudaGetLastError());
   }
-  {  // dHidden[n][h] = row_scale * (E[n][v] . W[v][h]) + onehot * W[label]   A = stash (K-major), B = W read transposed
+  // dHidden[n][h] = row_scale * (E[n][v] . W[v][h]) + onehot * W[label]   A = stash (K-major), B = W read transposed
+  bool dh_split = false;
+  if (dev.dh_split) {  // worth it when the tile count leaves the last round of CTA groups mostly idle
+    const uint32_t groups = static_cast<uint32_t>(dev.sms / dev.cta_group);
+    const uint32_t tiles = cdiv(n, tile_rows(dev.cta_group, dev.cta_group == 2 ? dev.ksub : 1)) * cdiv(h, kBlockN);
+    const uint32_t kb = static_cast<uint32_t>(w.stash_vb);
+    dh_split = groups > 0 && tiles % groups != 0 &&
+               100 * gemm_cost_split(tiles, groups, kb) <= 93 * gemm_cost_plain(tiles, groups < tiles ? groups : tiles, kb);
+  }
+  if (dh_split) {  // fp32 accumulator + split-K tail (the K slices of a tile add up in the reduce-add epilogue), then
+                   // the scale / one-hot / bf16 arithmetic of EpiBF16 in a fix-up pass over [n][h]
+    PhaseScope ps(PH_DH_GEMM, stream);
+    GRPO_CUDA(cudaMemsetAsync(w.dh_acc, 0, static_cast<size_t>(n) * h * sizeof(float), stream));
+    EpiF32<1, kBlockN>::Params p1;
+    memset(&p1, 0, sizeof(p1));
+    p1.c = w.dh_acc;
+    p1.ldc = h;
+    p1.m = un;
+    p1.n = uh;
+    p1.accumulate = 1u;
+    p1.use_tma = dev.dw_tma ? 1u : 0u;
+    p1.policy = kEvictNormal;  // read back by the fix-up pass right away
+    if (p1.use_tma) GRPO_TRY(make_tmap_f32_out(&p1.c_map, w.dh_acc, uh, un, uh));
+    EpiF32<2, kBlockN>::Params p2;
+    memcpy(&p2, &p1, sizeof(p1));
+    TileSched s{};
+    s.m_fast = static_cast<uint32_t>(dev.dh_m_fast);
+    s.sync_period = static_cast<uint32_t>(dev.sync_dh);
+    s.sync_ctr = w.sync + 1;
+    s.split_tail = 2;
+    s.probe = dev.clk_probe ? w.probe + 1024 : nullptr;
+    GRPO_TRY((launch_gemm_any<A_BLOCKED_K, true, EpiF32<1, kBlockN>, EpiF32<2, kBlockN>>(
+        dev, w.stash, n, w.stash_vb, weight, h, h, v, s, p1, p2, stream)));
+    const uint32_t vecs = un * (uh >> 3);
+    dh_fixup_kernel<<<cdiv(vecs, 256), 256, 0, stream>>>(w.dh_acc, factorised ? w.row_scale : nullptr,
+                                                         factorised ? w.onehot : nullptr, labels + r0, weight, un, uh,
+                                                         dhidden + r0 * h);
+    count_launch();
+    GRPO_CUDA(cudaGetLastError());
+  } else {
     PhaseScope ps(PH_DH_GEMM, stream);
     EpiBF16<1, kBlockN>::Params p1{dhidden + r0 * h, h, un, uh, factorised ? w.row_scale : nullptr,
                                    factorised ? w.onehot : nullptr, labels + r0, weight, h};
@@ -596,8 +693,9 @@ int grpo_set_option(const char* name, int value) {
   else if (!strcmp(name, "st_hint")) g_knobs.st_hint = value & 3;
   else if (!strcmp(name, "clk_probe")) g_knobs.clk_probe = value != 0;
   else if (!strcmp(name, "acc_lead")) g_knobs.acc_lead = value < 0 ? 0 : value;
-  else if (!strcmp(name, "dw_split")) g_knobs.dw_split = value != 0;
+  else if (!strcmp(name, "dw_split")) g_knobs.dw_split = value < 0 ? 0 : (value > 2 ? 2 : value);  // 2: grpo_debug_gemm runs the multi-round plan
   else if (!strcmp(name, "epi_share")) g_knobs.epi_share = value != 0;
+  else if (!strcmp(name, "dh_split")) g_knobs.dh_split = value != 0;
   else if (!strcmp(name, "chunk_rows")) g_knobs.chunk_rows = value > 0 ? (value + 511) / 512 * 512 : 0;
   else return fail(GRPO_ERR_ARG, "unknown option '%s'", name);
   return 0;
@@ -1197,6 +1295,34 @@ int grpo_logprob_from_logits_bwd(const void* logits, int logits_dtype, const int
   return 0;
 }
 
+int grpo_debug_plan_units(int64_t tiles, int64_t k_blocks, int groups_avail, int split_mode, int32_t* units,
+                          int64_t max_units, int32_t* info) {
+  if (tiles <= 0 || k_blocks <= 0 || groups_avail <= 0 || tiles > 0x7fffffffll || k_blocks > 0x7fffffffll)
+    return fail(GRPO_ERR_ARG, "bad dimensions");
+  if (split_mode < 0 || split_mode > 2) return fail(GRPO_ERR_ARG, "split_mode must be 0, 1 or 2");
+  TileSched s{};
+  s.k_blocks = static_cast<uint32_t>(k_blocks);
+  s.split_tail = static_cast<uint32_t>(split_mode);
+  const uint32_t groups = plan_units(s, static_cast<uint32_t>(tiles), static_cast<uint32_t>(groups_avail));
+  if (info) {
+    info[0] = static_cast<int32_t>(groups);
+    info[1] = static_cast<int32_t>(s.num_units);
+    info[2] = static_cast<int32_t>(s.max_progress);
+    info[3] = static_cast<int32_t>(s.split_slices);
+  }
+  if (units) {
+    if (static_cast<int64_t>(s.num_units) > max_units) return fail(GRPO_ERR_WORKSPACE, "units buffer too small");
+    for (uint32_t u = 0; u < s.num_units; ++u) {
+      uint32_t t, kb0, kb1;
+      decode_unit(s, u, t, kb0, kb1);
+      units[3 * u] = static_cast<int32_t>(t);
+      units[3 * u + 1] = static_cast<int32_t>(kb0);
+      units[3 * u + 2] = static_cast<int32_t>(kb1);
+    }
+  }
+  return 0;
+}
+
 int grpo_debug_gemm(const void* a, const void* b, float* c, int64_t m, int64_t n, int64_t k, int a_mn_major,
                     int b_mn_major, int cta_group, int accumulate, grpo_stream_t stream) {
   if (!a || !b || !c) return fail(GRPO_ERR_ARG, "null operand");
@@ -1220,7 +1346,7 @@ int grpo_debug_gemm(const void* a, const void* b, float* c, int64_t m, int64_t n
   memcpy(&p2, &p1, sizeof(p1));
   TileSched s{};
   s.m_fast = 1;
-  s.split_tail = (accumulate != 0 && dev.dw_split != 0) ? 1u : 0u;
+  s.split_tail = (accumulate != 0) ? static_cast<uint32_t>(dev.dw_split) : 0u;  // 2: the multi-round plan (dHidden split path)
   // A: 0 = [m][k], 1 = [k][m], 2 = blocked [m/64][k/64][64][64], 3 = blocked [k/64][m/64][64 k][64 m]
   const uint64_t a_pitch = a_mn_major == 0 ? k : (a_mn_major == 1 ? m : (a_mn_major == 2 ? (k + 63) / 64 : (m + 63) / 64));
   const uint64_t b_pitch = b_mn_major ? n : k;

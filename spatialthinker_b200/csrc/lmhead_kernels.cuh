@@ -407,6 +407,44 @@ __global__ void scale_scatter_kernel(const __nv_bfloat16* __restrict__ hidden, c
 }
 
 // ------------------------------------------------------------------------------------------
+// Fix-up pass of the dHidden GEMM's split-K path: the K slices were summed in fp32 by the reduce-add epilogue; this
+// applies what the direct bf16 epilogue (EpiBF16) does to a finished accumulator,
+//     dhidden[r][:] = bf16(row_scale[r] * acc[r][:] + onehot[r] * W[label_r][:])
+// (row_scale == nullptr: 1, onehot == nullptr: no gather term - the entropy-gradient mode). One thread per 8 columns.
+// ------------------------------------------------------------------------------------------
+__global__ void dh_fixup_kernel(const float* __restrict__ acc, const float* __restrict__ row_scale,
+                                const float* __restrict__ onehot, const int64_t* __restrict__ labels,
+                                const __nv_bfloat16* __restrict__ weight, uint32_t rows, uint32_t hdim,
+                                __nv_bfloat16* __restrict__ dhidden) {
+  const uint32_t vpr = hdim >> 3;  // 8-column vectors per row (hdim % 64 == 0)
+  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t row = idx / vpr;
+  if (row >= rows) return;
+  const uint32_t col = (idx - row * vpr) << 3;
+  const size_t off = static_cast<size_t>(row) * hdim + col;
+  const float4 a0 = *reinterpret_cast<const float4*>(acc + off);
+  const float4 a1 = *reinterpret_cast<const float4*>(acc + off + 4);
+  const float sc = row_scale ? row_scale[row] : 1.f;
+  const float oh = onehot ? onehot[row] : 0.f;
+  float f[8] = {a0.x * sc, a0.y * sc, a0.z * sc, a0.w * sc, a1.x * sc, a1.y * sc, a1.z * sc, a1.w * sc};
+  if (oh != 0.f) {  // onehot is 0 for rows whose label is out of range (scale_scatter_kernel)
+    const uint4 wv = *reinterpret_cast<const uint4*>(weight + static_cast<size_t>(labels[row]) * hdim + col);
+    const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      f[2 * i] = fmaf(oh, __uint_as_float(ww[i] << 16), f[2 * i]);
+      f[2 * i + 1] = fmaf(oh, __uint_as_float(ww[i] & 0xffff0000u), f[2 * i + 1]);
+    }
+  }
+  uint4 pk;
+  pk.x = pack_bf16x2(f[0], f[1]);
+  pk.y = pack_bf16x2(f[2], f[3]);
+  pk.z = pack_bf16x2(f[4], f[5]);
+  pk.w = pack_bf16x2(f[6], f[7]);
+  *reinterpret_cast<uint4*>(dhidden + off) = pk;
+}
+
+// ------------------------------------------------------------------------------------------
 // General backward preparation (entropy gradient requested): stash -> dL/dz in place (bf16)
 //    p = e / S;   dz[r][v] = scale * ( dlogp[r] * (1[v == label r] - p) - dent[r] * p * (log p + H r) )
 // after which the backward GEMMs run with unit scales. Rows whose upstream gradients are all zero are written as zeros

@@ -4,7 +4,9 @@ the CPU oracle and the golden vectors generated from the reference.
 Tolerances are the ones BASELINE.json's north_star states: per-token log-probs and entropy 2e-3 absolute,
 advantages 1e-6 (|a - a_ref| <= 1e-6 * max(1, |a_ref|)), loss and gradients 1e-2 relative (Frobenius for tensors).
 """
+import ctypes
 import math
+import os
 
 import numpy as np
 import pytest
@@ -16,6 +18,7 @@ pytestmark = pytest.mark.gpu
 
 CLIP = (0.2, 0.3, 3.0)
 EPI_SHARE_DEFAULT = 0  # library default of the "epi_share" option (restored by tests that toggle it)
+DH_SPLIT_DEFAULT = int(os.environ.get("GRPO_DH_SPLIT", "1") != "0")  # library default of "dh_split" (env override as in the library)
 TOL_LOGP = 2e-3
 TOL_ADV = 1e-6
 TOL_REL = 1e-2
@@ -141,6 +144,99 @@ def test_debug_gemm_split_k_tail(st, dev, cta, ksub_rows, a_mode, b_mn):
     np.testing.assert_allclose(outs[0].numpy(), outs[1].numpy(), rtol=0, atol=2e-3)  # fp32 summation order differs
 
 
+@pytest.mark.parametrize("shape", ["few_tiles", "big_remainder"])
+@pytest.mark.parametrize("a_mode,b_mn,tma", [(2, 1, 1), (0, 0, 1), (2, 1, 0)])
+def test_debug_gemm_multi_round_split(st, dev, shape, a_mode, b_mn, tma):
+    """Split-K plan of the dHidden GEMM's fp32 path (option dw_split = 2 on the debug entry): the tiles of the last partial
+    round - or ALL tiles when there are fewer tiles than CTA pairs - are cut along K into slices walked slice-major over
+    several short rounds; the accumulating epilogue adds the slices up. (2, 1) = blocked K-major A, B read transposed:
+    the operand layouts of the dHidden GEMM."""
+    from spatialthinker_b200 import _lib
+
+    lib = _lib.load()
+    if shape == "few_tiles":  # 3 x 2 wide tiles on 74 pairs, 24 K-blocks (ragged everywhere)
+        m, n, k = 3 * 512 - 37, 2 * 256 - 8, 64 * 23 + 40
+    else:  # 40 x 3 = 120 tiles on 74 pairs: remainder 46 > half a round, 64 K-blocks
+        m, n, k = 40 * 512 - 100, 3 * 256 - 16, 64 * 63 + 24
+    info = (ctypes.c_int32 * 4)()
+    _lib.check(lib.grpo_debug_plan_units(-(-m // 512) * -(-n // 256), -(-k // 64), 74, 2, None, 0, info), "plan")
+    assert info[3] > 1, "this shape is meant to take the split plan"
+    g = torch.Generator().manual_seed(23)
+    a = torch.randn(m, k, generator=g).to(torch.bfloat16)
+    b = torch.randn(n, k, generator=g).to(torch.bfloat16)
+    want = a.double() @ b.double().t() + 1.0
+    if a_mode == 2:  # blocked [m/64][k/64][64 m][64 k] image of A, as the dHidden GEMM reads the stash
+        kp, mp = (k + 63) // 64 * 64, (m + 63) // 64 * 64
+        pad = torch.zeros(mp, kp, dtype=torch.bfloat16)
+        pad[:m, :k] = a
+        a_d = pad.view(mp // 64, 64, kp // 64, 64).permute(0, 2, 1, 3).contiguous().to(dev)
+    else:
+        a_d = a.to(dev)
+    b_d = (b.t().contiguous() if b_mn else b).to(dev)
+    outs = []
+    for split in (2, 0):
+        c = torch.full((m + 8, n), 1.0, device=dev)  # 8 guard rows
+        _lib.check(lib.grpo_set_option(b"dw_split", split), "set_option")
+        _lib.check(lib.grpo_set_option(b"dw_tma", tma), "set_option")
+        try:
+            _lib.check(lib.grpo_debug_gemm(a_d.data_ptr(), b_d.data_ptr(), c.data_ptr(), m, n, k, a_mode, b_mn, 2, 1,
+                                           _lib.stream_ptr(dev)), "gemm")
+            torch.cuda.synchronize()
+        finally:
+            lib.grpo_set_option(b"dw_split", 1)
+            lib.grpo_set_option(b"dw_tma", 1)
+        assert bool((c[m:] == 1.0).all())
+        outs.append(c[:m].cpu())
+    np.testing.assert_allclose(outs[0].double().numpy(), want.numpy(), rtol=0, atol=5e-3)
+    np.testing.assert_allclose(outs[0].numpy(), outs[1].numpy(), rtol=0, atol=2e-3)  # fp32 summation order differs
+
+
+@pytest.mark.parametrize("rows,h,v", [(4096 - 33, 3584, 32768 + 72), (1100, 256, 2 * 4096 + 520), (9000, 512, 4096)])
+@pytest.mark.parametrize("dent", [False, True])
+def test_dhidden_split_path_matches_direct(st, dev, rows, h, v, dent):
+    """Option dh_split: when the dHidden GEMM's tiles are not a whole number of rounds over the CTA pairs it accumulates in
+    fp32 with a split-K tail and converts in a fix-up pass. Same gradients as the direct bf16 epilogue (bf16 rounding
+    of sums taken in a different order) and as the oracle. First shape = the reference's 4-sequence micro-batch at the
+    7B head width (8 x 14 tiles = 1.51 rounds), second = fewer tiles than pairs, third = 18 x 2 tiles."""
+    from spatialthinker_b200 import _lib
+
+    lib = _lib.load()
+    hid, w = O.synth_head(rows, h, v, seed=5, sigma_w=0.1)
+    g = torch.Generator().manual_seed(5)
+    lab = torch.randint(0, v, (rows,), generator=g)
+    lab[7] = -100  # a label no vocabulary row matches
+    gl = torch.randn(rows, generator=g) / rows
+    gl[::5] = 0.0  # masked rows
+    ge = torch.randn(rows, generator=g) / rows if dent else None
+    outs, launches = [], []
+    try:
+        for split in (1, 0):
+            _lib.check(lib.grpo_set_option(b"dh_split", split), "set_option")
+            n0 = lib.grpo_launch_count()
+            hd, wd = hid.to(dev).requires_grad_(True), w.to(dev).requires_grad_(True)
+            lp, ent = st.fused_lm_head_log_probs(hd, wd, lab.clamp_min(0).to(dev) if dent else lab.to(dev), 1.3,
+                                                 want_entropy=dent)
+            loss = (lp * gl.to(dev)).sum()
+            if dent:
+                loss = loss + (ent * ge.to(dev)).sum()
+            loss.backward()
+            torch.cuda.synchronize()
+            outs.append((hd.grad.clone(), wd.grad.clone()))
+            launches.append(lib.grpo_launch_count() - n0)
+    finally:
+        lib.grpo_set_option(b"dh_split", DH_SPLIT_DEFAULT)
+    assert launches[0] == launches[1] + 1, "the split path adds exactly the fix-up kernel (one chunk)"
+    assert rel(outs[0][0], outs[1][0]) < 2e-3  # bf16 outputs, fp32 sums in another order
+    assert rel(outs[0][1], outs[1][1]) < 1e-5  # dW does not go through the split path
+    if not dent:
+        valid = lab >= 0
+        hf, wf = hid.float().requires_grad_(True), w.float().requires_grad_(True)
+        lp_ref, _ = O.lm_head_log_probs(hf, wf, lab.clamp_min(0), 1.3)
+        (lp_ref * gl * valid).sum().backward()
+        keep = valid.nonzero().squeeze(1)
+        assert rel(outs[0][0][keep.to(dev)], hf.grad[keep]) < TOL_REL
+
+
 def test_epilogue_variants_agree(st, dev):
     """Softmax-epilogue variants (plain loop / pipelined TMEM drain / stash through bulk tensor stores) and dW-epilogue
     variants must give the same log-probs bit for bit and the same gradients up to fp32 accumulation order."""
@@ -157,6 +253,9 @@ def test_epilogue_variants_agree(st, dev):
     (lp_ref * gl).sum().backward()
     outs = {}
     try:
+        # dHidden is compared bit for bit below: keep it on its one-writer-per-tile epilogue (the split-K path sums the
+        # K slices of a tile in whatever order they finish; it has its own test)
+        _lib.check(lib.grpo_set_option(b"dh_split", 0), "set_option")
         # (epi_mode, dw_tma, acc_lead, epi_share); epi_share = both epilogue warpgroups on one accumulator at a time
         for epi, dwt, lead, share in ((0, 0, 0, 0), (1, 0, 0, 0), (3, 0, 1, 0), (3, 1, 2, 0), (0, 1, 3, 0), (7, 1, 2, 0),
                                       (0, 1, 2, 1), (1, 1, 0, 1), (3, 1, 2, 1), (7, 1, 2, 1), (7, 1, 3, 1)):
@@ -173,6 +272,7 @@ def test_epilogue_variants_agree(st, dev):
         lib.grpo_set_option(b"dw_tma", 1)
         lib.grpo_set_option(b"acc_lead", 2)
         lib.grpo_set_option(b"epi_share", EPI_SHARE_DEFAULT)
+        lib.grpo_set_option(b"dh_split", DH_SPLIT_DEFAULT)
     base = outs[(0, 0, 0, 0)]
     assert float((base[0].cpu() - lp_ref.detach()).abs().max()) < TOL_LOGP
     assert rel(base[1], hf.grad) < TOL_REL and rel(base[2], wf.grad) < TOL_REL

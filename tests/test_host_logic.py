@@ -194,3 +194,58 @@ def test_header_is_plain_c_and_links(lib, tmp_path):
     version, ws, rc, msg = out.stdout.split(maxsplit=3)
     assert int(version) == 1 and int(ws) == lib.grpo_fused_loss_workspace_bytes(37888, 3584, 151936)
     assert int(rc) == -1 and "null" in msg
+
+
+def _plan(lib, tiles, k_blocks, groups, mode):
+    info = (ctypes.c_int32 * 4)()
+    assert lib.grpo_debug_plan_units(tiles, k_blocks, groups, mode, None, 0, info) == 0
+    n_groups, n_units, bound, slices = list(info)
+    units = (ctypes.c_int32 * (3 * n_units))()
+    assert lib.grpo_debug_plan_units(tiles, k_blocks, groups, mode, units, n_units, info) == 0
+    return n_groups, np.array(units, dtype=np.int64).reshape(n_units, 3), bound, slices
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_work_unit_plan_covers_every_k_block_once(lib, mode):
+    """The persistent GEMMs walk `units` (whole tiles + split-K slices of the last partial round): every (tile, K-block)
+    must be covered exactly once, and no group may load more K-blocks than the progress-window bound handed to the
+    producers (an underestimate would leave a producer waiting for arrivals that never come)."""
+    rng = np.random.default_rng(5)
+    cases = [(112, 2374, 74), (28, 2374, 74), (4158, 296, 74), (518, 2374, 74), (1, 32, 74), (75, 2, 74), (80, 1, 74),
+             (149, 24, 148), (3, 7, 2), (73, 17, 74)]
+    cases += [(int(rng.integers(1, 700)), int(rng.integers(1, 300)), int(rng.integers(1, 149))) for _ in range(60)]
+    for tiles, kb, groups in cases:
+        n_groups, units, bound, slices = _plan(lib, tiles, kb, groups, mode)
+        assert 1 <= n_groups <= groups
+        cover = np.zeros((tiles, kb), dtype=np.int32)
+        load = np.zeros(n_groups, dtype=np.int64)
+        for u, (t, k0, k1) in enumerate(units):
+            assert 0 <= t < tiles and 0 <= k0 < k1 <= kb, (tiles, kb, groups, u, t, k0, k1)
+            cover[t, k0:k1] += 1
+            load[u % n_groups] += k1 - k0
+        assert (cover == 1).all(), (tiles, kb, groups, mode)
+        assert load.max() <= bound, (tiles, kb, groups, mode, load.max(), bound)
+        if mode == 0:
+            assert slices == 0 and len(units) == tiles
+        if mode == 1 and slices:  # one short extra round
+            assert len(units) - (tiles - tiles % n_groups) <= n_groups
+
+
+def test_split_plan_shortens_the_reference_micro_batch(lib):
+    """dHidden GEMM of the reference's shipped micro-batch (4 sequences x 1024 tokens, 7B head: 8 x 14 wide tiles on 74
+    CTA pairs = 1.51 rounds): whole tiles take 2 rounds, the split plan stays within 10 % of the ideal 1.51."""
+    tiles, kb, groups = 8 * 14, 2374, 74
+    n_groups, units, _, slices = _plan(lib, tiles, kb, groups, 2)
+    assert n_groups == groups and slices > 1
+    load = np.zeros(groups, dtype=np.int64)
+    for u, (_, k0, k1) in enumerate(units):
+        load[u % groups] += k1 - k0
+    assert load.max() < 1.10 * tiles * kb / groups
+    assert load.max() < 0.85 * 2 * kb
+    # slice-major tail: the groups running side by side in a tail round work on (at most two) common K ranges
+    tail = units[tiles - tiles % groups:]
+    first_round = tail[:groups]
+    assert len({(k0, k1) for _, k0, k1 in first_round.tolist()}) <= 2
+    # fewer tiles than groups: every group gets work
+    n_groups, units, _, slices = _plan(lib, 28, kb, groups, 2)
+    assert n_groups == groups and slices > 1 and len(units) > groups
