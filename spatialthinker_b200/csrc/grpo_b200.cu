@@ -201,7 +201,7 @@ struct Knobs {
   int st_hint = 3;     // bit 0: stash bulk stores evict-first, bit 1: dW bulk reduce-adds evict-first (else normal)
   int clk_probe = 0;   // 1: the GEMM kernels record clock64 / globaltimer at entry and exit (grpo_debug_probe_offset)
   int dw_tma = 1;      // dW GEMM epilogue: 1 = bulk tensor reduce-add from shared memory, 0 = per-thread red.global.add
-  int dw_split = 1;    // dW GEMM: split-K tail for the last, partial round of tiles (TileSched::split_tail)
+  int dw_split = 1;    // dW GEMM: split-K tail for the last, partial round of tiles (TileSched::split_tail; 2 = multi-round plan)
   int epi_share = 0;   // logits GEMM, wide tile: both epilogue warpgroups drain accumulator 0, then 1 (TileSched::epi_share)
   // dHidden GEMM: when its tile count is not a whole number of rounds over the CTA pairs (micro-batches that are not a
   // multiple of 37 row tiles, e.g. the reference's 4-sequence micro-batches), accumulate in fp32 with a split-K tail and
@@ -229,7 +229,8 @@ static void init_knobs() {
     g_knobs.wait_hint_ns = env_int("GRPO_WAIT_HINT_NS", g_knobs.wait_hint_ns);
     g_knobs.epi_mode = env_int("GRPO_EPI_MODE", g_knobs.epi_mode) & 7;
     g_knobs.dw_tma = env_int("GRPO_DW_TMA", g_knobs.dw_tma) != 0;
-    g_knobs.dw_split = env_int("GRPO_DW_SPLIT", g_knobs.dw_split) != 0;
+    g_knobs.dw_split = env_int("GRPO_DW_SPLIT", g_knobs.dw_split);
+    g_knobs.dw_split = g_knobs.dw_split < 0 ? 0 : (g_knobs.dw_split > 2 ? 2 : g_knobs.dw_split);
     g_knobs.epi_share = env_int("GRPO_EPI_SHARE", g_knobs.epi_share) != 0;
     g_knobs.dh_split = env_int("GRPO_DH_SPLIT", g_knobs.dh_split) != 0;
     g_knobs.acc_lead = env_int("GRPO_ACC_LEAD", g_knobs.acc_lead);
