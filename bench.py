@@ -156,6 +156,7 @@ def valid_counts(x, plan):
 
 
 ENTROPY_COEFF = 0.0  # --entropy-coeff: the upstream-veRL entropy bonus (0 in the reference, which only logs the entropy)
+DEFER = None  # --defer-dw: a fused.DeferredDW session (one dW GEMM per group of small micro-batches)
 
 
 def run_step_device(st, x, plan, dweight, world, temperature, want_entropy, counts=None):
@@ -172,8 +173,11 @@ def run_step_device(st, x, plan, dweight, world, temperature, want_entropy, coun
             res = st.grpo_micro_batch_step(x["hidden"][sl], x["weight"], x["labels"][sl], x["old"][sl], adv[sl], x["ref"][sl],
                                            x["mask"][sl], temperature=temperature, grad_accum=ga, dweight_accum=dweight,
                                            want_entropy=want_entropy, entropy_coeff=ENTROPY_COEFF,
-                                           valid_rows=None if counts is None else counts[(sl.start, sl.stop)], **CLIP, **KL)
+                                           valid_rows=None if counts is None else counts[(sl.start, sl.stop)],
+                                           defer=DEFER, **CLIP, **KL)
             metrics.append(res["metrics"])
+        if DEFER is not None:
+            DEFER.flush()
         allreduce_mean_(dweight)
         norms.append(torch.linalg.vector_norm(dweight))
         dweight.zero_()
@@ -236,10 +240,13 @@ def run_step_e2e(st, x, feed, plan, dweight, temperature, want_entropy, host_met
         res = st.grpo_micro_batch_step(mb["hidden"], x["weight"], mb["labels"], mb["old"], mb["adv"], mb["ref"], mb["mask"],
                                        temperature=temperature, grad_accum=float(len(plan[i])), dweight_accum=dweight,
                                        want_entropy=want_entropy, entropy_coeff=ENTROPY_COEFF,
-                                       valid_rows=None if counts is None else counts[(sl.start, sl.stop)], **CLIP, **KL)
+                                       valid_rows=None if counts is None else counts[(sl.start, sl.stop)],
+                                       defer=DEFER, **CLIP, **KL)
         feed.release(slot)
         metrics.append(res["metrics"])
         if j + 1 == len(flat) or flat[j + 1][0] != i:
+            if DEFER is not None:
+                DEFER.flush()
             allreduce_mean_(dweight)
             metrics.append(torch.linalg.vector_norm(dweight).expand(metrics[0].shape[0]))
             dweight.zero_()
@@ -323,6 +330,8 @@ def main():
     ap.add_argument("--sequences", type=int, default=0, help="override the rollout batch size (debug)")
     ap.add_argument("--entropy-coeff", type=float, default=0.0,
                     help="loss -= coeff * masked_mean(entropy): adds the per-element stash -> dlogits pass (not in the reference)")
+    ap.add_argument("--defer-dw", action="store_true",
+                    help="small micro-batches share one dW GEMM per group (fused.DeferredDW); no effect on the default plan")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -390,6 +399,10 @@ def main():
         return float(t.item())
 
     counts = valid_counts(x, plan)
+    if args.defer_dw:
+        global DEFER
+        from spatialthinker_b200.fused import DeferredDW
+        DEFER = DeferredDW(x["weight"], dweight)
     dev_step = lambda: run_step_device(st, x, plan, dweight, world, 1.0, want_entropy, counts)  # noqa: E731
     for _ in range(args.warmup):
         dev_step()
@@ -454,7 +467,7 @@ def main():
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
         "config": {"workload": f"{args.config}: {desc}", "hidden": hdim, "vocab": vocab, "sequences": bsz, "response_len": tlen,
-                   "group_n": n, "micro_batch_sequences": micro_seqs, "optimizer_steps_per_step": len(plan),
+                   "group_n": n, "micro_batch_sequences": micro_seqs, "optimizer_steps_per_step": len(plan), "defer_dw": bool(args.defer_dw),
                    "loss": "GRPO clip .2/.3/3.0 + low_var_kl 1e-2" + (f" - {args.entropy_coeff} * entropy" if args.entropy_coeff else ""), "l2": "inputs (>= 30 GB) far exceed the 126 MB L2",
                    "parallelism": f"dp{world} by sequence, dW mean all-reduce (NCCL)"},
         "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline, "e2e": e2e,

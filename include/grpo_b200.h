@@ -121,6 +121,32 @@ int grpo_fused_loss_fwd_bwd(const void* hidden, const void* weight, const int64_
                             grpo_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * Deferred dW for SMALL micro-batches (the reference ships micro_batch_size_per_device_for_update = 4,
+ * scripts/config.yaml; the gradient-accumulation loop is dp_actor.py:242-290). The weight gradient of the loop is a sum
+ * over micro-batches, so its GEMM need not run once per micro-batch: the exp-stash workspace holds one chunk of
+ * grpo_chunk_capacity_rows() rows anyway, and several small micro-batches can each run forward + loss + dHidden in
+ * their own window ("slot") of it and share ONE dW GEMM over all collected rows - dW is then read-modify-written once
+ * and the GEMM's K is long enough to hide its fp32 drain.
+ *   grpo_fused_loss_fwd_bwd_slot: grpo_fused_loss_fwd_bwd for rows placed at [slot_row0, slot_row0 + rows) of a
+ *     workspace of capacity_rows rows (capacity_rows % 512 == 0, <= grpo_chunk_capacity_rows(); slot_row0 % 512 == 0;
+ *     workspace sized by grpo_fused_loss_workspace_bytes(capacity_rows, ...)). Everything except the stash-dependent
+ *     part of dW is final on return (log-probs, metrics, dhidden, the one-hot rows of dW). No entropy gradient
+ *     (entropy_out is output only). The caller must not use the workspace for anything else until the flush.
+ *   grpo_deferred_dw_flush: dweight += stash^T . scaled hidden over rows [0, total_rows), where total_rows is the end of
+ *     the last slot and consecutive slots start at the previous end rounded up to 512.
+ * ------------------------------------------------------------------------------------------------------------------ */
+long long grpo_chunk_capacity_rows(void);
+int grpo_fused_loss_fwd_bwd_slot(const void* hidden, const void* weight, const int64_t* labels, const float* old_logp,
+                                 const float* advantages, const float* ref_logp, const void* mask, int mask_dtype,
+                                 int64_t rows, int64_t hidden_dim, int64_t vocab, float temperature,
+                                 float clip_ratio_low, float clip_ratio_high, float clip_ratio_dual, int kl_mode,
+                                 float kl_coef, float grad_accum, float* logp_out, float* entropy_out, void* dhidden,
+                                 float* dweight, float* metrics, int64_t slot_row0, int64_t capacity_rows,
+                                 void* workspace, size_t workspace_bytes, grpo_stream_t stream);
+int grpo_deferred_dw_flush(int64_t total_rows, int64_t capacity_rows, int64_t hidden_dim, int64_t vocab, float* dweight,
+                           void* workspace, size_t workspace_bytes, grpo_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Token-level policy loss on given log-probs (no lm_head): the four masked means of compute_policy_loss
  * (core_algos.py:291-353), optionally the KL term (compute_kl :394-436) and dL/dlogp with
  * L = (pg + kl_coef * kl) / grad_accum.   acc_scratch: 8 doubles of device scratch.

@@ -20,7 +20,7 @@ from .core_algos import (  # noqa: F401
     kl_penalty,
 )
 from .dp_actor import ActorConfig, DataParallelPPOActor  # noqa: F401
-from .fused import fused_grpo_loss, fused_lm_head_log_probs, grpo_micro_batch_step  # noqa: F401
+from .fused import DeferredDW, fused_grpo_loss, fused_lm_head_log_probs, grpo_micro_batch_step  # noqa: F401
 from .patch import patch_verl, unpatch_verl  # noqa: F401
 from .protocol import TensorBatch  # noqa: F401
 from .ray_trainer import AdvantageEstimator, apply_kl_penalty, compute_advantage, experience_pass  # noqa: F401

@@ -44,6 +44,13 @@ _SIGNATURES = {
         [_P, _P, _P, _P, _P, _P, _P, c_int, c_int64, c_int64, c_int64, c_float, c_float, c_float, c_float, c_int,
          c_float, c_float, c_float, _P, _P, _P, _P, _P, _P, c_size_t, _P],
     ),
+    "grpo_chunk_capacity_rows": (ctypes.c_longlong, []),
+    "grpo_fused_loss_fwd_bwd_slot": (
+        c_int,
+        [_P, _P, _P, _P, _P, _P, _P, c_int, c_int64, c_int64, c_int64, c_float, c_float, c_float, c_float, c_int,
+         c_float, c_float, _P, _P, _P, _P, _P, c_int64, c_int64, _P, c_size_t, _P],
+    ),
+    "grpo_deferred_dw_flush": (c_int, [c_int64, c_int64, c_int64, c_int64, _P, _P, c_size_t, _P]),
     "grpo_policy_loss_fwd_bwd": (
         c_int,
         [_P, _P, _P, _P, _P, c_int, c_int64, c_float, c_float, c_float, c_int, c_float, c_float, _P, _P, _P, _P],

@@ -397,6 +397,7 @@ struct Workspace {
   // sizes for one chunk of rows
   int64_t chunk_rows = 0, rows_pad = 0, n_tiles = 0;
   int64_t stash_vb = 0;                // 64-column blocks per stash row block = ceil(V / 64)
+  int64_t stash_rows = 0;              // rows the stash holds from its base pointer (rows_pad; less in a slot view)
   // exp(z - z_label) (entropy-gradient mode: rewritten to dL/dz), BLOCKED: [rows_pad/64][stash_vb][64 rows][64 cols].
   // 8 KB contiguous per block, so both backward GEMMs - one walking vocab blocks as K, the other row blocks as K -
   // stream it from HBM in whole DRAM pages instead of 128-byte pieces 300 KB apart.
@@ -421,6 +422,7 @@ static Workspace carve(void* base, int64_t rows, int64_t hdim, int64_t vocab, bo
   w.chunk_rows = rows < chunk_cap ? rows : chunk_cap;
   if (w.chunk_rows < 1) w.chunk_rows = 1;
   w.rows_pad = static_cast<int64_t>(align_up(static_cast<size_t>(w.chunk_rows), 512));
+  w.stash_rows = w.rows_pad;
   w.n_tiles = (vocab + kBlockN - 1) / kBlockN;
   size_t off = 0;
   uint8_t* p = static_cast<uint8_t*>(base);
@@ -455,6 +457,28 @@ static Workspace carve(void* base, int64_t rows, int64_t hdim, int64_t vocab, bo
   return w;
 }
 
+// A window of a chunk workspace that starts `row0` rows in (row0 % 512 == 0: whole tiles): the stash, the scaled hidden
+// rows and every per-row array are shifted, leading dimensions stay. Several small micro-batches can then each run
+// forward + dHidden in their own window of ONE chunk's stash and share a single dW GEMM over all of its rows
+// (grpo_fused_loss_fwd_bwd_slot / grpo_deferred_dw_flush).
+static Workspace slot_view(const Workspace& w, int64_t row0, int64_t hdim) {
+  Workspace v = w;
+  v.stash = w.stash + static_cast<size_t>(row0 / 64) * w.stash_vb * 4096;
+  v.stash_rows = w.rows_pad - row0;
+  v.hd_scaled = w.hd_scaled + static_cast<size_t>(row0) * hdim;
+  v.part_sum = w.part_sum + row0;
+  v.part_ez = w.part_ez + row0;
+  v.a_label = w.a_label + row0;
+  v.lse = w.lse + row0;
+  v.inv_sum = w.inv_sum + row0;
+  v.dlogp = w.dlogp + row0;
+  v.dent = w.dent + row0;
+  v.ent = w.ent + row0;
+  v.row_scale = w.row_scale + row0;
+  v.onehot = w.onehot + row0;
+  return v;
+}
+
 static int check_head_args(const void* hidden, const void* weight, int64_t rows, int64_t h, int64_t v, float temp) {
   if (!hidden || !weight) return fail(GRPO_ERR_ARG, "hidden / weight must not be null");
   if (rows < 0 || h <= 0 || v <= 0) return fail(GRPO_ERR_ARG, "negative or zero dimension");
@@ -487,10 +511,10 @@ static int chunk_forward(const DevInfo& dev, const Workspace& w, const __nv_bflo
   if (!(p1.mode & 2)) p1.mode &= 3u;
   if (p1.mode & 2)  // store view of the blocked stash: 32 rows x 64 columns (4 KB, contiguous in HBM) per bulk store
     GRPO_TRY(make_tmap_blocked(&p1.stash_map, w.stash, static_cast<uint64_t>(w.stash_vb),
-                               static_cast<uint64_t>(w.rows_pad / 64), static_cast<uint64_t>(w.stash_vb), 1, 1, 32));
+                               static_cast<uint64_t>(w.stash_rows / 64), static_cast<uint64_t>(w.stash_vb), 1, 1, 32));
   if (p1.mode & 4)  // ... or 32 rows x 32 columns (64-byte pieces of 32 consecutive 128-byte rows) per bulk store
     GRPO_TRY(make_tmap_blocked(&p1.stash_map_half, w.stash, static_cast<uint64_t>(w.stash_vb),
-                               static_cast<uint64_t>(w.rows_pad / 64), static_cast<uint64_t>(w.stash_vb), 1, 1, 32, 32));
+                               static_cast<uint64_t>(w.stash_rows / 64), static_cast<uint64_t>(w.stash_vb), 1, 1, 32, 32));
   p1.rows = static_cast<uint32_t>(n);
   p1.vocab = static_cast<uint32_t>(v);
   p1.rows_pad = static_cast<uint32_t>(w.rows_pad);
@@ -535,13 +559,47 @@ static int chunk_forward(const DevInfo& dev, const Workspace& w, const __nv_bflo
   return 0;
 }
 
+// dW[v][h] += E^T[v][n] . hd[n][h]    A = the stash's first n rows read transposed (MN-major), B = (scaled) hidden read
+// transposed. The fp32 epilogue accumulates (bulk reduce-add), so a call adds one group of rows' contribution to `dweight`.
+static int dw_gemm(const DevInfo& dev, const Workspace& w, const __nv_bfloat16* b_op, int64_t n, int64_t h, int64_t v,
+                   float* dweight, cudaStream_t stream) {
+  const uint32_t uh = static_cast<uint32_t>(h), uv = static_cast<uint32_t>(v);
+  PhaseScope ps(PH_DW_GEMM, stream);
+  EpiF32<1, kBlockN>::Params p1;
+  memset(&p1, 0, sizeof(p1));
+  p1.c = dweight;
+  p1.ldc = h;
+  p1.m = uv;
+  p1.n = uh;
+  p1.accumulate = 1u;
+  p1.use_tma = dev.dw_tma ? 1u : 0u;
+  p1.policy = (dev.st_hint & 2) ? kEvictFirst : kEvictNormal;
+  if (p1.use_tma) GRPO_TRY(make_tmap_f32_out(&p1.c_map, dweight, uh, uv, uh));
+  EpiF32<2, kBlockN>::Params p2;
+  static_assert(sizeof(p1) == sizeof(p2), "epilogue params layout");
+  memcpy(&p2, &p1, sizeof(p1));
+  TileSched s{};
+  s.m_fast = 0;  // the H column blocks of one vocab block run together: the stash panel is read from HBM once
+  s.sync_period = static_cast<uint32_t>(dev.sync_dw);
+  s.sync_ctr = w.sync + 2;
+  s.split_tail = static_cast<uint32_t>(dev.dw_split);  // the epilogue accumulates (reduce-add): K slices just add up
+  s.probe = dev.clk_probe ? w.probe + 2048 : nullptr;
+  if (dev.l2_hints & 2) {  // the (scaled) hidden chunk is re-read for every vocab block; the stash streams through once
+    s.hint_a = kEvictFirst;
+    s.hint_b = kEvictLast;
+  }
+  GRPO_TRY((launch_gemm_any<A_BLOCKED_MN, true, EpiF32<1, kBlockN>, EpiF32<2, kBlockN>>(
+      dev, w.stash, v, w.stash_vb, b_op, h, h, n, s, p1, p2, stream)));
+  return 0;
+}
+
 // dHidden = dlogits . W and dW += dlogits^T . hidden for rows [r0, r0 + n), from the stash of chunk_forward.
 //   dent == nullptr (the GRPO loss): dlogits factorises per row, the stash is used as is (scale_scatter_kernel).
 //   dent != nullptr (entropy gradient): the stash is first rewritten into dlogits (stash_to_dlogits_kernel).
 static int chunk_backward(const DevInfo& dev, const Workspace& w, const __nv_bfloat16* hidden,
                           const __nv_bfloat16* weight, const int64_t* labels, const float* dlogp, const float* dent,
                           const float* ent, int64_t r0, int64_t n, int64_t h, int64_t v, float temperature,
-                          __nv_bfloat16* dhidden, float* dweight, cudaStream_t stream) {
+                          __nv_bfloat16* dhidden, float* dweight, cudaStream_t stream, bool skip_dw = false) {
   const bool factorised = dent == nullptr;
   const uint32_t un = static_cast<uint32_t>(n), uh = static_cast<uint32_t>(h), uv = static_cast<uint32_t>(v);
   {
@@ -611,34 +669,9 @@ static int chunk_backward(const DevInfo& dev, const Workspace& w, const __nv_bfl
     GRPO_TRY((launch_gemm_any<A_BLOCKED_K, true, EpiBF16<1, kBlockN>, EpiBF16<2, kBlockN>>(
         dev, w.stash, n, w.stash_vb, weight, h, h, v, s, p1, p2, stream)));
   }
-  {  // dW[v][h] += E^T[v][n] . hd[n][h]    A = stash read transposed (MN-major), B = (scaled) hidden read transposed
-    PhaseScope ps(PH_DW_GEMM, stream);
-    EpiF32<1, kBlockN>::Params p1;
-    memset(&p1, 0, sizeof(p1));
-    p1.c = dweight;
-    p1.ldc = h;
-    p1.m = uv;
-    p1.n = uh;
-    p1.accumulate = 1u;
-    p1.use_tma = dev.dw_tma ? 1u : 0u;
-    p1.policy = (dev.st_hint & 2) ? kEvictFirst : kEvictNormal;
-    if (p1.use_tma) GRPO_TRY(make_tmap_f32_out(&p1.c_map, dweight, uh, uv, uh));
-    EpiF32<2, kBlockN>::Params p2;
-    static_assert(sizeof(p1) == sizeof(p2), "epilogue params layout");
-    memcpy(&p2, &p1, sizeof(p1));
-    TileSched s{};
-    s.m_fast = 0;  // the H column blocks of one vocab block run together: the stash panel is read from HBM once
-    s.sync_period = static_cast<uint32_t>(dev.sync_dw);
-    s.sync_ctr = w.sync + 2;
-    s.split_tail = static_cast<uint32_t>(dev.dw_split);  // the epilogue accumulates (reduce-add): K slices just add up
-    s.probe = dev.clk_probe ? w.probe + 2048 : nullptr;
-    if (dev.l2_hints & 2) {  // the (scaled) hidden chunk is re-read for every vocab block; the stash streams through once
-      s.hint_a = kEvictFirst;
-      s.hint_b = kEvictLast;
-    }
+  if (!skip_dw) {
     const __nv_bfloat16* b_op = factorised ? w.hd_scaled : hidden + r0 * h;
-    GRPO_TRY((launch_gemm_any<A_BLOCKED_MN, true, EpiF32<1, kBlockN>, EpiF32<2, kBlockN>>(
-        dev, w.stash, v, w.stash_vb, b_op, h, h, n, s, p1, p2, stream)));
+    GRPO_TRY(dw_gemm(dev, w, b_op, n, h, v, dweight, stream));
   }
   return 0;
 }
@@ -787,13 +820,12 @@ int grpo_lmhead_bwd(const void* hidden, const void* weight, const int64_t* label
   return 0;
 }
 
-int grpo_fused_loss_fwd_bwd(const void* hidden, const void* weight, const int64_t* labels, const float* old_logp,
-                            const float* advantages, const float* ref_logp, const void* mask, int mask_dtype,
-                            int64_t rows, int64_t hidden_dim, int64_t vocab, float temperature, float clip_ratio_low,
-                            float clip_ratio_high, float clip_ratio_dual, int kl_mode, float kl_coef,
-                            float entropy_coef, float grad_accum, float* logp_out, float* entropy_out, void* dhidden,
-                            float* dweight, float* metrics, void* workspace, size_t workspace_bytes,
-                            grpo_stream_t stream) {
+// Argument checks shared by the fused-loss entry points.
+static int check_fused_loss_args(const void* hidden, const void* weight, const int64_t* labels, const float* old_logp,
+                                 const float* advantages, const float* ref_logp, const void* mask, int mask_dtype,
+                                 int64_t rows, int64_t hidden_dim, int64_t vocab, float temperature, int kl_mode,
+                                 float entropy_coef, float grad_accum, const float* logp_out, const float* entropy_out,
+                                 const void* dhidden, const float* dweight, const float* metrics) {
   GRPO_TRY(check_head_args(hidden, weight, rows, hidden_dim, vocab, temperature));
   if (!labels || !old_logp || !advantages || !logp_out || !metrics)
     return fail(GRPO_ERR_ARG, "labels / old_logp / advantages / logp_out / metrics must not be null");
@@ -805,14 +837,18 @@ int grpo_fused_loss_fwd_bwd(const void* hidden, const void* weight, const int64_
   if (kl_mode != GRPO_KL_NONE && !ref_logp) return fail(GRPO_ERR_ARG, "kl_mode set but ref_logp is null");
   if (entropy_coef != 0.f && !entropy_out) return fail(GRPO_ERR_ARG, "entropy_coef != 0 needs entropy_out");
   if (!(grad_accum > 0.f)) return fail(GRPO_ERR_ARG, "grad_accum must be positive");
-  DevInfo dev;
-  GRPO_TRY(get_dev(&dev));
+  return 0;
+}
+
+// One micro-batch through workspace (view) `w`: mask sum, then per chunk forward -> token loss -> backward, then the
+// metric vector. skip_dw: leave the stash-dependent part of dW to a later dw_gemm over the whole workspace.
+static int fused_loss_body(const DevInfo& dev, const Workspace& w, const void* hidden, const void* weight,
+                           const int64_t* labels, const float* old_logp, const float* advantages,
+                           const float* ref_logp, const void* mask, int mask_dtype, int64_t rows, int64_t hidden_dim,
+                           int64_t vocab, float temperature, const LossCfg& cfg, float* logp_out, float* entropy_out,
+                           void* dhidden, float* dweight, float* metrics, bool skip_dw, cudaStream_t stream) {
   const bool want_bwd = dhidden != nullptr;
-  const Workspace w = carve(workspace, rows, hidden_dim, vocab, true);
-  if (!workspace || workspace_bytes < w.bytes)
-    return fail(GRPO_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
-  LossCfg cfg = make_loss_cfg(clip_ratio_low, clip_ratio_high, clip_ratio_dual, kl_mode, kl_coef, grad_accum);
-  cfg.entropy_coef = entropy_coef;
+  const float entropy_coef = cfg.entropy_coef;
   auto* hp = static_cast<const __nv_bfloat16*>(hidden);
   auto* wp = static_cast<const __nv_bfloat16*>(weight);
   const size_t esz = (mask_dtype == MASK_F32) ? 4 : (mask_dtype == MASK_I64 ? 8 : 1);
@@ -843,12 +879,103 @@ int grpo_fused_loss_fwd_bwd(const void* hidden, const void* weight, const int64_
     if (want_bwd)
       GRPO_TRY(chunk_backward(dev, w, hp, wp, labels, w.dlogp, entropy_coef != 0.f ? w.dent : nullptr,
                               want_ent ? entropy_out + r0 : nullptr, r0, n, hidden_dim, vocab, temperature,
-                              static_cast<__nv_bfloat16*>(dhidden), dweight, stream));
+                              static_cast<__nv_bfloat16*>(dhidden), dweight, stream, skip_dw));
   }
   loss_finalize_kernel<<<1, 32, 0, stream>>>(w.acc, cfg, metrics);
   count_launch();
   GRPO_CUDA(cudaGetLastError());
   return 0;
+}
+
+int grpo_fused_loss_fwd_bwd(const void* hidden, const void* weight, const int64_t* labels, const float* old_logp,
+                            const float* advantages, const float* ref_logp, const void* mask, int mask_dtype,
+                            int64_t rows, int64_t hidden_dim, int64_t vocab, float temperature, float clip_ratio_low,
+                            float clip_ratio_high, float clip_ratio_dual, int kl_mode, float kl_coef,
+                            float entropy_coef, float grad_accum, float* logp_out, float* entropy_out, void* dhidden,
+                            float* dweight, float* metrics, void* workspace, size_t workspace_bytes,
+                            grpo_stream_t stream) {
+  GRPO_TRY(check_fused_loss_args(hidden, weight, labels, old_logp, advantages, ref_logp, mask, mask_dtype, rows,
+                                 hidden_dim, vocab, temperature, kl_mode, entropy_coef, grad_accum, logp_out,
+                                 entropy_out, dhidden, dweight, metrics));
+  DevInfo dev;
+  GRPO_TRY(get_dev(&dev));
+  const Workspace w = carve(workspace, rows, hidden_dim, vocab, true);
+  if (!workspace || workspace_bytes < w.bytes)
+    return fail(GRPO_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
+  LossCfg cfg = make_loss_cfg(clip_ratio_low, clip_ratio_high, clip_ratio_dual, kl_mode, kl_coef, grad_accum);
+  cfg.entropy_coef = entropy_coef;
+  return fused_loss_body(dev, w, hidden, weight, labels, old_logp, advantages, ref_logp, mask, mask_dtype, rows,
+                         hidden_dim, vocab, temperature, cfg, logp_out, entropy_out, dhidden, dweight, metrics, false,
+                         stream);
+}
+
+long long grpo_chunk_capacity_rows(void) {
+  init_knobs();
+  return g_knobs.chunk_rows > 0 ? g_knobs.chunk_rows : default_chunk_rows(g_knobs.cta_group, g_knobs.ksub);
+}
+
+// Workspace of the deferred-dW entry points: one chunk of `capacity_rows` rows (a multiple of 512, at most one chunk).
+static int carve_deferred(Workspace* w, void* workspace, size_t workspace_bytes, int64_t capacity_rows,
+                          int64_t hidden_dim, int64_t vocab) {
+  if (capacity_rows <= 0 || capacity_rows % 512 != 0 || capacity_rows > grpo_chunk_capacity_rows())
+    return fail(GRPO_ERR_ARG, "capacity_rows must be a positive multiple of 512, at most grpo_chunk_capacity_rows()");
+  *w = carve(workspace, capacity_rows, hidden_dim, vocab, true);
+  if (!workspace || workspace_bytes < w->bytes)
+    return fail(GRPO_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", w->bytes, workspace_bytes);
+  return 0;
+}
+
+int grpo_fused_loss_fwd_bwd_slot(const void* hidden, const void* weight, const int64_t* labels, const float* old_logp,
+                                 const float* advantages, const float* ref_logp, const void* mask, int mask_dtype,
+                                 int64_t rows, int64_t hidden_dim, int64_t vocab, float temperature,
+                                 float clip_ratio_low, float clip_ratio_high, float clip_ratio_dual, int kl_mode,
+                                 float kl_coef, float grad_accum, float* logp_out, float* entropy_out, void* dhidden,
+                                 float* dweight, float* metrics, int64_t slot_row0, int64_t capacity_rows,
+                                 void* workspace, size_t workspace_bytes, grpo_stream_t stream) {
+  GRPO_TRY(check_fused_loss_args(hidden, weight, labels, old_logp, advantages, ref_logp, mask, mask_dtype, rows,
+                                 hidden_dim, vocab, temperature, kl_mode, 0.f, grad_accum, logp_out, entropy_out,
+                                 dhidden, dweight, metrics));
+  if (!dhidden) return fail(GRPO_ERR_ARG, "the slot entry is the training path: dhidden / dweight must be given");
+  if (rows <= 0) return fail(GRPO_ERR_ARG, "a slot needs at least one row");
+  if (slot_row0 < 0 || slot_row0 % 512 != 0 || slot_row0 + rows > capacity_rows)
+    return fail(GRPO_ERR_ARG, "slot [%lld, %lld) does not fit the workspace of %lld rows (slot_row0 %% 512 == 0)",
+                (long long)slot_row0, (long long)(slot_row0 + rows), (long long)capacity_rows);
+  DevInfo dev;
+  GRPO_TRY(get_dev(&dev));
+  Workspace full;
+  GRPO_TRY(carve_deferred(&full, workspace, workspace_bytes, capacity_rows, hidden_dim, vocab));
+  const Workspace w = slot_view(full, slot_row0, hidden_dim);
+  const LossCfg cfg = [&] {
+    LossCfg c = make_loss_cfg(clip_ratio_low, clip_ratio_high, clip_ratio_dual, kl_mode, kl_coef, grad_accum);
+    c.entropy_coef = 0.f;  // an entropy gradient rewrites the stash and needs the hidden rows at dW time: not deferrable
+    return c;
+  }();
+  GRPO_TRY(fused_loss_body(dev, w, hidden, weight, labels, old_logp, advantages, ref_logp, mask, mask_dtype, rows,
+                           hidden_dim, vocab, temperature, cfg, logp_out, entropy_out, dhidden, dweight, metrics, true,
+                           stream));
+  // rows between this slot's end and the next 512-row boundary: their stash rows were written as zeros by the logits
+  // GEMM (it stores every row of its tiles); the scaled-hidden rows they meet in the deferred dW GEMM must be finite
+  const int64_t end = slot_row0 + rows;
+  int64_t gap_end = (end + 511) / 512 * 512;
+  if (gap_end > capacity_rows) gap_end = capacity_rows;
+  if (gap_end > end)
+    GRPO_CUDA(cudaMemsetAsync(full.hd_scaled + static_cast<size_t>(end) * hidden_dim, 0,
+                              static_cast<size_t>(gap_end - end) * hidden_dim * sizeof(__nv_bfloat16), stream));
+  return 0;
+}
+
+int grpo_deferred_dw_flush(int64_t total_rows, int64_t capacity_rows, int64_t hidden_dim, int64_t vocab, float* dweight,
+                           void* workspace, size_t workspace_bytes, grpo_stream_t stream) {
+  if (!dweight) return fail(GRPO_ERR_ARG, "dweight must not be null");
+  if (hidden_dim <= 0 || hidden_dim % 64 != 0 || vocab <= 0 || vocab % 8 != 0)
+    return fail(GRPO_ERR_ARG, "bad hidden_dim / vocab");
+  if (total_rows < 0 || total_rows > capacity_rows) return fail(GRPO_ERR_ARG, "total_rows exceeds capacity_rows");
+  if (total_rows == 0) return 0;
+  DevInfo dev;
+  GRPO_TRY(get_dev(&dev));
+  Workspace w;
+  GRPO_TRY(carve_deferred(&w, workspace, workspace_bytes, capacity_rows, hidden_dim, vocab));
+  return dw_gemm(dev, w, w.hd_scaled, total_rows, hidden_dim, vocab, dweight, stream);
 }
 
 int grpo_policy_loss_fwd_bwd(const float* logp, const float* old_logp, const float* advantages, const float* ref_logp,

@@ -25,7 +25,7 @@ import torch
 import torch.distributed as dist
 
 from . import _lib
-from .fused import compact_index, fused_lm_head_log_probs, gather_rows, grpo_micro_batch_step, scatter_rows
+from .fused import DeferredDW, compact_index, fused_lm_head_log_probs, gather_rows, grpo_micro_batch_step, scatter_rows
 from .sharding import allreduce_mean_
 
 __all__ = ["ActorConfig", "DataParallelPPOActor", "append_to_dict"]
@@ -74,6 +74,7 @@ class DataParallelPPOActor:
         hidden_fn: Optional[Callable[[Dict[str, Any]], torch.Tensor]] = None,
         process_group: Optional["dist.ProcessGroup"] = None,
         compact_padding: bool = True,
+        defer_dw: bool = True,
     ):
         self.config = config
         self.rank = int(os.getenv("RANK", "0"))
@@ -84,6 +85,12 @@ class DataParallelPPOActor:
         # drop padded token rows before the GEMMs (costs ONE device->host read of the per-micro-batch token counts per
         # update_policy call; the reference computes log-probs for padding and multiplies them by 0)
         self.compact_padding = compact_padding
+        # one dW GEMM per group of small micro-batches instead of one per micro-batch (fused.DeferredDW): pays when
+        # micro-batches are well below one 18944-row chunk, as with the reference's micro_batch_size_per_device_for_update = 4
+        # (+2.6 % tokens/s there, profiles/r1_ab_defer_dw.log); larger micro-batches take the ordinary path unchanged.
+        # Costs one more chunk workspace (6 GB at the 7B head).
+        self.defer_dw = defer_dw
+        self._deferred: Optional[DeferredDW] = None
         self.dweight: Optional[torch.Tensor] = None  # fp32 [V, H] accumulator ("main grad") across micro-batches
         self.last_dhidden: List[torch.Tensor] = []   # per micro-batch dHidden of the last update (when no hidden_fn)
 
@@ -177,6 +184,11 @@ class DataParallelPPOActor:
 
         if self.dweight is None:
             self.dweight = torch.zeros(self.weight.shape, dtype=torch.float32, device=self.weight.device)
+        defer = None
+        if self.defer_dw and cfg.entropy_coeff == 0.0:
+            if self._deferred is None or self._deferred.dweight is not self.dweight:
+                self._deferred = DeferredDW(self.weight.detach(), self.dweight)
+            defer = self._deferred
         pending: List[torch.Tensor] = []  # device metric vectors, one per micro-batch
         norms: List[torch.Tensor] = []
         self.last_dhidden = []
@@ -200,13 +212,15 @@ class DataParallelPPOActor:
                         temperature=temperature, clip_ratio_low=cfg.clip_ratio_low, clip_ratio_high=cfg.clip_ratio_high,
                         clip_ratio_dual=cfg.clip_ratio_dual, kl_penalty=cfg.kl_penalty if use_ref else None,
                         kl_coef=cfg.kl_coef, grad_accum=float(grad_accum), entropy_coeff=cfg.entropy_coeff,
-                        dweight_accum=self.dweight, valid_rows=valid_rows,
+                        dweight_accum=self.dweight, valid_rows=valid_rows, defer=defer,
                     )
                     if hidden.requires_grad:
                         hidden.backward(step["dhidden"])  # continue into the transformer body
                     else:
                         self.last_dhidden.append(step["dhidden"])
                     pending.append(step["metrics"])
+                if defer is not None:
+                    defer.flush()  # dW complete before it is all-reduced and applied
                 norms.append(self._optimizer_step())
 
         # one device->host transfer for every scalar of this call

@@ -102,6 +102,65 @@ def fused_lm_head_log_probs(
 
 
 # ----------------------------------------------------------------------------------------------------------------
+# deferred dW for small micro-batches
+# ----------------------------------------------------------------------------------------------------------------
+class DeferredDW:
+    """One chunk workspace shared by several SMALL micro-batches of a gradient-accumulation loop (dp_actor.py:242-290).
+
+    ``dW`` of the loop is a sum over its micro-batches, so the GEMM that produces it need not run once per micro-batch
+    (the reference ships ``micro_batch_size_per_device_for_update: 4``, scripts/config.yaml:28). Each micro-batch handed
+    to :func:`grpo_micro_batch_step` with ``defer=session`` runs forward + loss + dHidden in its own 512-row-aligned
+    window of the session's exp-stash; :meth:`flush` runs ONE dW GEMM over everything collected - ``dW`` is
+    read-modify-written once and the GEMM's K dimension is long enough to hide its fp32 drain. Everything but the
+    stash-dependent part of ``dW`` (log-probs, metrics, dHidden) is final when the step returns. Call :meth:`flush`
+    before ``dweight`` is read (optimizer step, all-reduce); a micro-batch that does not fit flushes first, one larger
+    than the workspace takes the ordinary path. No entropy gradient on this path (``entropy_coeff`` must be 0).
+    """
+
+    def __init__(self, weight: torch.Tensor, dweight_accum: torch.Tensor):
+        dev = require_cuda(weight, dweight_accum)
+        if dweight_accum.shape != weight.shape or dweight_accum.dtype != torch.float32 or not dweight_accum.is_contiguous():
+            raise ValueError("dweight_accum must be a contiguous float32 tensor shaped like weight")
+        lib = _lib.load()
+        self.device = dev
+        self.dweight = dweight_accum
+        self.vocab, self.hdim = weight.shape
+        self.capacity = int(lib.grpo_chunk_capacity_rows())
+        self.nbytes = int(lib.grpo_fused_loss_workspace_bytes(self.capacity, self.hdim, self.vocab))
+        # its own buffer: the stash must survive other head calls (compute_log_prob ...) between two micro-batches
+        # (zeroed once: stash rows no launch has written yet meet zero operand rows in the dW GEMM and must be finite)
+        self.workspace = torch.zeros(self.nbytes, dtype=torch.uint8, device=dev)
+        self.next_row0 = 0   # where the next slot starts (multiple of 512)
+        self.total_rows = 0  # end of the last slot
+        self.pending = 0     # micro-batches collected since the last flush
+
+    def reserve(self, rows: int) -> Optional[int]:
+        """Start row of a slot for ``rows`` rows (flushing first when the workspace is full); None when ``rows`` can
+        never fit and the caller should take the ordinary path."""
+        if rows <= 0 or rows > self.capacity:
+            return None
+        if self.next_row0 + rows > self.capacity:
+            self.flush()
+        row0 = self.next_row0
+        self.total_rows = row0 + rows
+        self.next_row0 = -(-self.total_rows // 512) * 512
+        self.pending += 1
+        return row0
+
+    def flush(self) -> None:
+        """dweight += stash^T . scaled hidden over every row collected since the last flush."""
+        if self.pending:
+            with torch.cuda.device(self.device):
+                _lib.check(
+                    _lib.load().grpo_deferred_dw_flush(self.total_rows, self.capacity, self.hdim, self.vocab,
+                                                       self.dweight.data_ptr(), self.workspace.data_ptr(),
+                                                       self.workspace.numel(), _lib.stream_ptr(self.device)),
+                    "grpo_deferred_dw_flush",
+                )
+        self.next_row0 = self.total_rows = self.pending = 0
+
+
+# ----------------------------------------------------------------------------------------------------------------
 # one micro-batch of the actor update, no autograd
 # ----------------------------------------------------------------------------------------------------------------
 METRIC_KEYS = {
@@ -134,6 +193,7 @@ def grpo_micro_batch_step(
     dweight_accum: Optional[torch.Tensor] = None,
     need_grads: bool = True,
     valid_rows: Optional[int] = None,
+    defer: Optional[DeferredDW] = None,
 ) -> Dict[str, torch.Tensor]:
     """Forward + backward of one micro-batch (dp_actor.py:247-278) entirely on the device, no host sync.
 
@@ -147,6 +207,9 @@ def grpo_micro_batch_step(
     them (dp_actor.py:136-139) - and the outputs are scattered back (``log_probs`` / ``entropy`` are 0 and ``dhidden``
     rows are 0 at padded positions). Without the hint nothing is compacted, because finding the count would cost a
     device->host sync.
+
+    ``defer`` (optional :class:`DeferredDW` built on ``dweight_accum``): the stash-dependent part of ``dweight`` is left
+    to ``defer.flush()``; everything else is final on return.
     """
     if valid_rows is not None and 0 < valid_rows < response_mask.numel():
         return _compacted_step(hidden, weight, labels, old_log_probs, advantages, ref_log_probs, response_mask,
@@ -154,7 +217,7 @@ def grpo_micro_batch_step(
                                                      clip_ratio_high=clip_ratio_high, clip_ratio_dual=clip_ratio_dual,
                                                      kl_penalty=kl_penalty, kl_coef=kl_coef, grad_accum=grad_accum,
                                                      entropy_coeff=entropy_coeff, want_entropy=want_entropy,
-                                                     dweight_accum=dweight_accum, need_grads=need_grads))
+                                                     dweight_accum=dweight_accum, need_grads=need_grads, defer=defer))
     dev, h2, w2, lab = _check_head(hidden, weight, labels)
     lib = _lib.load()
     rows, hdim = h2.shape
@@ -183,6 +246,33 @@ def grpo_micro_batch_step(
             dw = dweight_accum
         else:
             dw = torch.zeros(vocab, hdim, dtype=torch.float32, device=dev)
+    slot_row0 = None
+    if defer is not None:
+        if not need_grads or dw is not defer.dweight or entropy_coeff != 0.0:
+            raise ValueError("defer needs need_grads=True, dweight_accum=defer.dweight and entropy_coeff == 0")
+        if (defer.hdim, defer.vocab) != (hdim, vocab) or defer.device != dev:
+            raise ValueError("defer was built for another weight")
+        slot_row0 = defer.reserve(rows)  # None: larger than the workspace - ordinary path below
+    if slot_row0 is not None:
+        with torch.cuda.device(dev):
+            _lib.check(
+                lib.grpo_fused_loss_fwd_bwd_slot(
+                    h2.data_ptr(), w2.data_ptr(), lab.data_ptr(), old.data_ptr(), adv.data_ptr(), _lib.ptr(ref),
+                    mask.data_ptr(), code, rows, hdim, vocab, float(temperature), float(clip_ratio_low),
+                    float(clip_ratio_high), float(clip_ratio_dual), mode, float(kl_coef if use_kl else 0.0),
+                    float(grad_accum), logp.data_ptr(), _lib.ptr(ent), dh.data_ptr(), dw.data_ptr(),
+                    metrics.data_ptr(), slot_row0, defer.capacity, defer.workspace.data_ptr(),
+                    defer.workspace.numel(), _lib.stream_ptr(dev)),
+                "grpo_fused_loss_fwd_bwd_slot",
+            )
+        return {
+            "log_probs": logp.view(*lead),
+            "entropy": ent.view(*lead) if ent is not None else None,
+            "metrics": metrics,
+            "dhidden": dh.view(hidden.shape),
+            "dweight": dw,
+            "used_kl": use_kl,
+        }
     nbytes = lib.grpo_fused_loss_workspace_bytes(rows, hdim, vocab)
     ws = scratch("head", dev, nbytes)
     with torch.cuda.device(dev):

@@ -749,6 +749,105 @@ def test_update_policy_matches_reference_loop(st, dev):
     np.testing.assert_allclose(met2["actor/pg_loss"], met["actor/pg_loss"], rtol=1e-6)
 
 
+def test_deferred_dw_matches_per_micro_batch(st, dev):
+    """fused.DeferredDW: several small micro-batches share one chunk workspace (each in its own 512-row-aligned slot) and
+    ONE dW GEMM at flush time. Log-probs and metrics are the per-micro-batch ones bit for bit (same kernels on the same
+    rows), dHidden and dW agree up to fp32 summation order, and dW matches the oracle's accumulated gradient. Slot
+    sizes are ragged so that the gaps up to the next 512-row boundary are exercised; the last micro-batch no longer
+    fits and forces a flush in the middle."""
+    from spatialthinker_b200 import _lib
+    from spatialthinker_b200.fused import DeferredDW
+
+    lib = _lib.load()
+    h, v = 256, 4096 + 520
+    _lib.check(lib.grpo_set_option(b"chunk_rows", 4096), "set_option")  # a small workspace: 4 slots, then it is full
+    try:
+        assert lib.grpo_chunk_capacity_rows() == 4096
+        sizes = [(7, 100), (4, 128), (9, 140), (1, 90), (6, 200)]  # (sequences, tokens) -> 700, 512, 1260, 90, 1200 rows
+        _, w = O.synth_head(8, h, v, seed=200, sigma_w=0.1)
+        cases = []
+        for i, (b, tl) in enumerate(sizes):  # every micro-batch against the SAME weight
+            hid, _ = O.synth_head(b * tl, h, v, seed=201 + i, sigma_w=0.1)
+            hid = hid.view(b, tl, h)
+            roll = O.synth_rollout(b, tl, v, b, seed=201 + i, ragged=(i % 2 == 0))
+            logp, _ = O.lm_head_log_probs(hid, w, roll["responses"], 0.9)
+            g = torch.Generator().manual_seed(300 + i)
+            adv = torch.randn(b, 1, generator=g).expand(b, tl) * roll["response_mask"]
+            cases.append({"hidden": hid, "labels": roll["responses"], "mask": roll["response_mask"], "adv": adv.contiguous(),
+                          "old": O.perturbed_log_probs(logp, seed=400 + i, outlier_frac=0.03),
+                          "ref": O.perturbed_log_probs(logp, seed=500 + i, outlier_frac=0.03)})
+        wd = w.to(dev)
+        kw = dict(temperature=0.9, kl_penalty="low_var_kl", kl_coef=0.01, grad_accum=float(len(cases)),
+                  clip_ratio_low=CLIP[0], clip_ratio_high=CLIP[1], clip_ratio_dual=CLIP[2], want_entropy=True)
+
+        def run(deferred):
+            dw = torch.zeros(v, h, dtype=torch.float32, device=dev)
+            session = DeferredDW(wd, dw) if deferred else None
+            outs, row0s = [], []
+            for x in cases:
+                res = st.grpo_micro_batch_step(x["hidden"].to(dev), wd, x["labels"].to(dev), x["old"].to(dev),
+                                               x["adv"].to(dev), x["ref"].to(dev), x["mask"].to(dev), dweight_accum=dw,
+                                               defer=session, **kw)
+                outs.append((res["log_probs"].clone(), res["entropy"].clone(), res["metrics"].clone(), res["dhidden"].clone()))
+                if session is not None:
+                    row0s.append(session.total_rows - x["labels"].numel())
+            if session is not None:
+                assert session.pending == 1  # the fifth micro-batch did not fit: flushed, then slot 0 again
+                session.flush()
+                assert session.pending == 0 and session.total_rows == 0
+            torch.cuda.synchronize()
+            return outs, dw, row0s
+
+        base, dw_base, _ = run(False)
+        got, dw_got, row0s = run(True)
+        assert row0s == [0, 1024, 1536, 3072, 0]
+        for (lp0, e0, m0, dh0), (lp1, e1, m1, dh1) in zip(base, got):
+            assert torch.equal(lp0, lp1) and torch.equal(e0, e1) and torch.equal(m0, m1)
+            assert rel(dh1, dh0) < 2e-3
+        assert rel(dw_got, dw_base) < 1e-4
+        want_dw = torch.zeros(v, h)
+        for x in cases:
+            want = O.fused_loss_reference(x["hidden"], w, x["labels"], x["old"], x["adv"], x["mask"], x["ref"],
+                                          temperature=0.9, kl_penalty="low_var_kl", kl_coef=0.01,
+                                          grad_accum=float(len(cases)))
+            want_dw += want["dweight"]
+        assert rel(dw_got, want_dw) < TOL_REL
+    finally:
+        lib.grpo_set_option(b"chunk_rows", 0)
+
+
+def test_update_policy_deferred_dw(st, dev):
+    """DataParallelPPOActor(defer_dw=True): same metrics, same dW per optimizer step, same dHidden as the default loop."""
+    bsz, tl, h, v = 16, 48, 128, 4096
+    x = _loss_inputs(bsz, tl, h, v, 4, 0.1, seed=81, ragged=True)
+    cfg = st.ActorConfig(global_batch_size_per_device=8, micro_batch_size_per_device_for_update=2,
+                         micro_batch_size_per_device_for_experience=4, use_kl_loss=True, kl_penalty="low_var_kl", kl_coef=0.01)
+    tensors = {"responses": x["labels"].to(dev), "response_mask": x["mask"].to(dev), "advantages": x["adv"].to(dev),
+               "old_log_probs": x["old"].to(dev), "ref_log_probs": x["ref"].to(dev), "hidden_states": x["hidden"].to(dev)}
+    data = st.TensorBatch(tensors, meta_info={"temperature": 0.9})
+    res = []
+    for defer in (False, True):
+        actor = st.DataParallelPPOActor(cfg, x["weight"].to(dev), defer_dw=defer)
+        dws = []
+        orig = actor._optimizer_step
+
+        def spy(actor=actor, dws=dws, orig=orig):
+            dws.append(actor.dweight.clone())
+            return orig()
+
+        actor._optimizer_step = spy
+        met = actor.update_policy(data)
+        res.append((met, dws, torch.cat(list(actor.last_dhidden), dim=0)))
+    (m0, dw0, dh0), (m1, dw1, dh1) = res
+    assert len(dw0) == len(dw1) == 2
+    for key in ("actor/pg_loss", "actor/entropy_loss", "actor/ppo_kl", "actor/pg_clipfrac_higher"):
+        assert m0[key] == m1[key], key
+    for a, b in zip(dw0, dw1):
+        assert rel(b, a) < 1e-4
+    np.testing.assert_allclose(m1["actor/grad_norm"], m0["actor/grad_norm"], rtol=1e-4)
+    assert rel(dh1, dh0) < 2e-3
+
+
 def test_update_policy_with_hidden_fn_and_optimizer(st, dev):
     """hidden_fn keeps an autograd graph: dHidden must reach the parameters behind it, and the optimizer must move W."""
     bsz, tl, h, v = 8, 16, 64, 1024
