@@ -249,3 +249,25 @@ def test_split_plan_shortens_the_reference_micro_batch(lib):
     # fewer tiles than groups: every group gets work
     n_groups, units, _, slices = _plan(lib, 28, kb, groups, 2)
     assert n_groups == groups and slices > 1 and len(units) > groups
+
+
+def test_deferred_dw_slot_bookkeeping():
+    """fused.DeferredDW.reserve: slots start on 512-row boundaries, a micro-batch that no longer fits flushes first, one
+    larger than the workspace is refused (the caller then takes the ordinary path). Pure host arithmetic."""
+    from spatialthinker_b200.fused import DeferredDW
+
+    s = object.__new__(DeferredDW)  # no device: only the bookkeeping is exercised
+    s.capacity, s.next_row0, s.total_rows, s.pending = 18944, 0, 0, 0
+    flushed = []
+
+    def flush():
+        flushed.append((s.total_rows, s.pending))
+        s.next_row0 = s.total_rows = s.pending = 0
+
+    s.flush = flush
+    assert [s.reserve(n) for n in (4096, 4000, 100, 4096)] == [0, 4096, 8192, 8704]
+    assert (s.total_rows, s.next_row0, s.pending) == (12800, 12800, 4) and not flushed
+    assert s.reserve(6144) == 12800 and s.total_rows == 18944  # exactly full
+    assert s.reserve(1) == 0 and flushed == [(18944, 5)]  # did not fit: flushed, first slot again
+    assert s.reserve(18945) is None and s.reserve(0) is None  # never fits / empty: ordinary path
+    assert (s.total_rows, s.next_row0, s.pending) == (1, 512, 1)
