@@ -252,19 +252,22 @@ def grpo_micro_batch_step(
             raise ValueError("defer needs need_grads=True, dweight_accum=defer.dweight and entropy_coeff == 0")
         if (defer.hdim, defer.vocab) != (hdim, vocab) or defer.device != dev:
             raise ValueError("defer was built for another weight")
+        before = (defer.next_row0, defer.total_rows, defer.pending)
         slot_row0 = defer.reserve(rows)  # None: larger than the workspace - ordinary path below
     if slot_row0 is not None:
         with torch.cuda.device(dev):
-            _lib.check(
-                lib.grpo_fused_loss_fwd_bwd_slot(
-                    h2.data_ptr(), w2.data_ptr(), lab.data_ptr(), old.data_ptr(), adv.data_ptr(), _lib.ptr(ref),
-                    mask.data_ptr(), code, rows, hdim, vocab, float(temperature), float(clip_ratio_low),
-                    float(clip_ratio_high), float(clip_ratio_dual), mode, float(kl_coef if use_kl else 0.0),
-                    float(grad_accum), logp.data_ptr(), _lib.ptr(ent), dh.data_ptr(), dw.data_ptr(),
-                    metrics.data_ptr(), slot_row0, defer.capacity, defer.workspace.data_ptr(),
-                    defer.workspace.numel(), _lib.stream_ptr(dev)),
-                "grpo_fused_loss_fwd_bwd_slot",
-            )
+            rc = lib.grpo_fused_loss_fwd_bwd_slot(
+                h2.data_ptr(), w2.data_ptr(), lab.data_ptr(), old.data_ptr(), adv.data_ptr(), _lib.ptr(ref),
+                mask.data_ptr(), code, rows, hdim, vocab, float(temperature), float(clip_ratio_low),
+                float(clip_ratio_high), float(clip_ratio_dual), mode, float(kl_coef if use_kl else 0.0),
+                float(grad_accum), logp.data_ptr(), _lib.ptr(ent), dh.data_ptr(), dw.data_ptr(),
+                metrics.data_ptr(), slot_row0, defer.capacity, defer.workspace.data_ptr(),
+                defer.workspace.numel(), _lib.stream_ptr(dev))
+        if rc != 0:
+            # the slot was not (completely) filled: give it back, or the flush would sum whatever an earlier group left
+            # there. (slot_row0 != before[0]: reserve() flushed first and this was the first slot of a new group.)
+            defer.next_row0, defer.total_rows, defer.pending = before if slot_row0 == before[0] else (0, 0, 0)
+        _lib.check(rc, "grpo_fused_loss_fwd_bwd_slot")
         return {
             "log_probs": logp.view(*lead),
             "entropy": ent.view(*lead) if ent is not None else None,
