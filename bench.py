@@ -1,19 +1,29 @@
 """bench.py - GRPO loss fwd+bwd response-tokens/s on the Qwen2.5-VL-7B head shape (BASELINE.json metric / configs[2]).
 
     python bench.py --gpus 1 --steps K --warmup W            # this library, one process per GPU (torchrun for N > 1)
-    python bench.py --impl reference --steps K --warmup W    # the reference arithmetic on the host cores (oracle port)
+    python bench.py --impl reference --steps K --warmup W    # the reference's own torch functions on the host cores
 
-One "step" = one pass of the hot path over one rollout batch: group-normalised advantages, then for every micro-batch
-lm_head -> log-probs -> clipped policy loss + low_var_kl -> dHidden and dW (accumulated in fp32), then per optimizer
-step the mean all-reduce of dW over ranks and its norm (dp_actor.py:155-167 minus the optimizer update itself, which is
-outside the path). The rollout batch of 512 prompts x n=8 x 1024 response tokens is sharded by sequence over the ranks
-(strong scaling: total work fixed).
+One "step" = one pass of the hot path over one rollout batch, driven through the drop-in for the reference's actor,
+``DataParallelPPOActor.update_policy`` (verl/workers/actor/dp_actor.py:212-292): group-normalised advantages, then for
+every micro-batch lm_head -> log-probs -> clipped policy loss + low_var_kl -> dHidden and dW (accumulated in fp32), then
+per optimizer step the mean all-reduce of dW over ranks and its norm (dp_actor.py:155-167 minus the optimizer update
+itself, which is outside the path), metrics read back to the host. The rollout batch of 512 prompts x n=8 x 1024 response
+tokens is sharded by sequence over the ranks (strong scaling: total work fixed); micro-batches are formed by token count
+(``use_dynamic_bsz``, 37 888 tokens = two 18 944-row chunks) unless ``--micro-seqs`` asks for the reference's fixed size.
+
+Synthetic inputs follow SURVEY.md section 8(d): ``old_log_probs = logp + 0.1 randn`` with 1 % of the entries shifted by
++-1.5 (both clip sides, the dual clip and the KL clamp are hit), ``ref_log_probs`` likewise, where ``logp`` comes from one
+forward pass of the head in setup - so dL/dlogp is non-zero on essentially every token (``--legacy-inputs`` restores
+round 1's ``-3 + 0.1 randn``, under which half of the gradient rows are exact zeros).
 
 `value`  : tokens/s with every input already resident in HBM (CUDA events, max over ranks).
-`e2e`    : the same pass driven from PINNED HOST buffers through the public API: every micro-batch's inputs are copied
-           host->device inside the timed region (double-buffered on a copy stream) and the step's metrics are read back.
+`e2e`    : the same pass with the rollout batch in PINNED HOST memory: rewards go host->device, advantages are computed
+           and read back, and ``update_policy`` streams every micro-batch's inputs host->device inside the timed region
+           (double-buffered on a copy stream); the metrics come back to the host.
 `roofline`: the dominant kernel's algorithmic FLOP/s (2*H*V per row) over its CUDA-event duration, live, against the
            measured bf16 tensor peak in MEASURED_PEAKS.json.
+`config.records`: the same device-resident pass at the reference's shipped micro-batch of 4 sequences
+           (scripts/config.yaml:28) with the deferred dW GEMM, on a few steps.
 """
 from __future__ import annotations
 
@@ -46,6 +56,7 @@ METRIC = "GRPO loss fwd+bwd response-tokens/s (7B head)"
 CLIP = dict(clip_ratio_low=0.2, clip_ratio_high=0.3, clip_ratio_dual=3.0)
 KL = dict(kl_penalty="low_var_kl", kl_coef=1e-2)
 OPT_STEPS = 4  # optimizer steps per rollout step: 4096 sequences / (global batch 128 x n 8), scripts/config.yaml:27
+MAX_TOKENS = 37888  # tokens per micro-batch: two 18 944-row chunks of the GEMM pipeline
 
 
 def load_peaks():
@@ -97,12 +108,38 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------------------------
-# synthetic workload, generated per rank on the device
+# synthetic workload: the GLOBAL batch structure (lengths, uids, rank assignment) is generated
+# identically on every rank, this rank's tensors on its device
 # ------------------------------------------------------------------------------------------------------------------
-def make_inputs(cfg, rank, world, dev, micro_seqs, ragged):
+def global_layout(cfg, world, ragged, balance):
+    """Response lengths and uids of the whole rollout batch, reordered so that rank r owns rows [r*local, (r+1)*local):
+    token-balanced with equal sequence counts exactly like the reference's driver does before dispatch
+    (_balance_batch, verl/trainer/ray_trainer.py:526-541 -> seqlen_balancing.py:150-181) when the batch is ragged."""
+    from spatialthinker_b200.sharding import balanced_partitions
+
+    _, _, bsz, tlen, n, _ = cfg
+    gp = torch.Generator().manual_seed(7)
+    uid = torch.arange(bsz // n).repeat_interleave(n)[torch.randperm(bsz, generator=gp)]  # permuted: groups straddle ranks
+    if ragged:
+        lens = (1 + torch.floor(torch.rand(bsz, generator=gp) * tlen)).clamp(max=tlen).long()
+    else:
+        lens = torch.full((bsz,), tlen, dtype=torch.long)
+    local = bsz // world
+    naive = [int(lens[r * local:(r + 1) * local].sum()) for r in range(world)]
+    if ragged and balance and world > 1:
+        parts = balanced_partitions(lens.tolist(), world, equal_size=True)
+        order = torch.tensor([i for p in parts for i in p])
+        lens, uid = lens[order], uid[order]
+    per_rank = [int(lens[r * local:(r + 1) * local].sum()) for r in range(world)]
+    return lens, uid.numpy(), per_rank, naive
+
+
+def make_inputs(st, cfg, rank, world, dev, ragged, legacy, balance):
     hdim, vocab, bsz, tlen, n, _ = cfg
     assert bsz % world == 0
     local = bsz // world
+    lens_all, uid_all, per_rank, naive = global_layout(cfg, world, ragged, balance)
+    lens = lens_all[rank * local:(rank + 1) * local].to(dev)
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     gw = torch.Generator(device=dev).manual_seed(99)  # the weight is replicated: same seed on every rank
     weight = torch.empty(vocab, hdim, dtype=torch.bfloat16, device=dev)
@@ -110,60 +147,66 @@ def make_inputs(cfg, rank, world, dev, micro_seqs, ragged):
         r1 = min(vocab, r0 + 16384)
         weight[r0:r1] = (0.02 * torch.randn(r1 - r0, hdim, generator=gw, device=dev)).to(torch.bfloat16)
     hidden = torch.empty(local, tlen, hdim, dtype=torch.bfloat16, device=dev)
-    for s0 in range(0, local, 8):
-        s1 = min(local, s0 + 8)
+    blk = max(1, 8192 // tlen)
+    for s0 in range(0, local, blk):
+        s1 = min(local, s0 + blk)
         hidden[s0:s1] = torch.randn(s1 - s0, tlen, hdim, generator=g, device=dev).to(torch.bfloat16)
     labels = torch.randint(0, vocab, (local, tlen), generator=g, device=dev)
-    if ragged:
-        lens = (1 + torch.floor(torch.rand(local, generator=g, device=dev) * tlen)).clamp(max=tlen).long()
-    else:
-        lens = torch.full((local,), tlen, dtype=torch.long, device=dev)
     mask = (torch.arange(tlen, device=dev)[None, :] < lens[:, None]).long()
-    score = torch.rand(local, generator=g, device=dev)
+    # reward = 0.1 f + 0.2 c + 0.5 a + 0.2 s with Bernoulli / uniform components (spatial_sgg.py:653-681), at the last token
+    comp = torch.rand(local, 4, generator=g, device=dev)
+    score = 0.1 * (comp[:, 0] > 0.2).float() + 0.2 * comp[:, 1] + 0.5 * (comp[:, 2] > 0.5).float() + 0.2 * comp[:, 3]
     rewards = torch.zeros(local, tlen, device=dev)
     rewards[torch.arange(local, device=dev), lens - 1] = score
-    # uid: prompt id repeated n, rows permuted globally (groups straddle ranks), this rank's slice
-    gp = torch.Generator().manual_seed(7)
-    uid_all = torch.arange(bsz // n).repeat_interleave(n)[torch.randperm(bsz, generator=gp)]
-    # old / ref log-probs: a plausible level with jitter (their exact values do not change the work done)
-    old = -3.0 + 0.1 * torch.randn(local, tlen, generator=g, device=dev)
-    ref = -3.0 + 0.1 * torch.randn(local, tlen, generator=g, device=dev)
-    return {"weight": weight, "hidden": hidden, "labels": labels, "mask": mask, "rewards": rewards, "uid_np": uid_all.numpy(),
-            "old": old, "ref": ref, "local": local, "lens": lens}
+    if legacy:  # round 1: a plausible level with jitter; every A < 0 token then sits on the clip and has dL/dlogp == 0
+        old = -3.0 + 0.1 * torch.randn(local, tlen, generator=g, device=dev)
+        ref = -3.0 + 0.1 * torch.randn(local, tlen, generator=g, device=dev)
+    else:  # the policy's own log-probs (one forward pass of the head) + jitter + 1 % outliers of +-1.5
+        logp = torch.empty(local, tlen, dtype=torch.float32, device=dev)
+        blk = max(1, MAX_TOKENS // tlen)
+        for s0 in range(0, local, blk):
+            logp[s0:s0 + blk], _ = st.fused_lm_head_log_probs(hidden[s0:s0 + blk], weight, labels[s0:s0 + blk], 1.0)
+
+        def perturbed():
+            out = logp + 0.1 * torch.randn(local, tlen, generator=g, device=dev)
+            hit = torch.rand(local, tlen, generator=g, device=dev) < 0.01
+            sign = torch.where(torch.rand(local, tlen, generator=g, device=dev) < 0.5, -1.5, 1.5)
+            return torch.where(hit, out + sign, out)
+
+        old, ref = perturbed(), perturbed()
+        del logp
+    return {"weight": weight, "hidden": hidden, "labels": labels, "mask": mask, "rewards": rewards, "uid_np": uid_all,
+            "old": old, "ref": ref, "local": local, "lens": lens, "tokens_per_rank": per_rank, "tokens_per_rank_unbalanced": naive}
 
 
-def step_plan(local, micro_seqs):
-    """(optimizer step, [micro-batch slices]) - mini-batches of local/OPT_STEPS sequences, micro-batches of micro_seqs."""
+def actor_config(st, local, micro_seqs, want_entropy, entropy_coeff):
     mini = max(local // OPT_STEPS, 1)
-    plan = []
-    for s0 in range(0, local, mini):
-        s1 = min(local, s0 + mini)
-        mbs = [slice(m0, min(m0 + micro_seqs, s1)) for m0 in range(s0, s1, micro_seqs)]
-        plan.append(mbs)
-    return plan
+    kw = dict(global_batch_size_per_device=mini, use_kl_loss=True, kl_penalty=KL["kl_penalty"], kl_coef=KL["kl_coef"],
+              log_true_entropy=want_entropy, entropy_coeff=entropy_coeff, **CLIP)
+    if micro_seqs:
+        return st.ActorConfig(micro_batch_size_per_device_for_update=micro_seqs, **kw)
+    return st.ActorConfig(use_dynamic_bsz=True, max_token_len_per_micro_batch=MAX_TOKENS, **kw)
 
 
 # ------------------------------------------------------------------------------------------------------------------
-# one step, device-resident inputs
+# one step through the actor, device-resident inputs
 # ------------------------------------------------------------------------------------------------------------------
-def valid_counts(x, plan):
-    """Host-side count of unmasked tokens per micro-batch (the trainer knows the response lengths); None when dense."""
-    lens = x["lens"].cpu()
-    tlen = x["mask"].shape[1]
-    if bool((lens == tlen).all()):
-        return None
-    return {(sl.start, sl.stop): int(lens[sl].sum()) for mbs in plan for sl in mbs}
-
-
-ENTROPY_COEFF = 0.0  # --entropy-coeff: the upstream-veRL entropy bonus (0 in the reference, which only logs the entropy)
-DEFER = None  # --defer-dw: a fused.DeferredDW session (one dW GEMM per group of small micro-batches)
-
-
-def run_step_device(st, x, plan, dweight, world, temperature, want_entropy, counts=None):
-    from spatialthinker_b200.sharding import allreduce_mean_
-
+def run_step_device(st, actor, x, world):
     # advantages: groups straddle ranks, so the per-sequence scores are all-gathered (B floats) and the group statistics
     # run redundantly per rank; this rank's rows are then broadcast over its response mask
+    rank = dist.get_rank() if world > 1 else 0
+    adv, _ = st.core_algos.compute_grpo_outcome_advantage_sharded(x["rewards"], x["mask"], x["uid_np"], rank * x["local"])
+    data = st.TensorBatch({"hidden_states": x["hidden"], "responses": x["labels"], "response_mask": x["mask"],
+                           "old_log_probs": x["old"], "ref_log_probs": x["ref"], "advantages": adv},
+                          meta_info={"temperature": 1.0})
+    return actor.update_policy(data)
+
+
+# the round-1 loop (no actor object): kept for A/B against the drop-in (--direct)
+def run_step_direct(st, x, plan, dweight, world, want_entropy, entropy_coeff, counts):
+    from spatialthinker_b200.dp_actor import grad_sumsq
+    from spatialthinker_b200.sharding import allreduce_mean_
+
     rank = dist.get_rank() if world > 1 else 0
     adv, _ = st.core_algos.compute_grpo_outcome_advantage_sharded(x["rewards"], x["mask"], x["uid_np"], rank * x["local"])
     metrics, norms = [], []
@@ -171,94 +214,84 @@ def run_step_device(st, x, plan, dweight, world, temperature, want_entropy, coun
         ga = float(len(mbs))
         for sl in mbs:
             res = st.grpo_micro_batch_step(x["hidden"][sl], x["weight"], x["labels"][sl], x["old"][sl], adv[sl], x["ref"][sl],
-                                           x["mask"][sl], temperature=temperature, grad_accum=ga, dweight_accum=dweight,
-                                           want_entropy=want_entropy, entropy_coeff=ENTROPY_COEFF,
-                                           valid_rows=None if counts is None else counts[(sl.start, sl.stop)],
-                                           defer=DEFER, **CLIP, **KL)
+                                           x["mask"][sl], temperature=1.0, grad_accum=ga, dweight_accum=dweight,
+                                           want_entropy=want_entropy, entropy_coeff=entropy_coeff,
+                                           valid_rows=None if counts is None else counts[(sl.start, sl.stop)], **CLIP, **KL)
             metrics.append(res["metrics"])
-        if DEFER is not None:
-            DEFER.flush()
         allreduce_mean_(dweight)
-        norms.append(torch.linalg.vector_norm(dweight))
-        dweight.zero_()
-    return torch.stack(metrics), torch.stack(norms)
+        norms.append(grad_sumsq(dweight, zero_after=True).sqrt())
+    return torch.stack(metrics).cpu(), torch.stack(norms).cpu()
+
+
+def direct_plan(x, micro_seqs):
+    local = x["local"]
+    mini = max(local // OPT_STEPS, 1)
+    plan = [[slice(m0, min(m0 + micro_seqs, s0 + mini)) for m0 in range(s0, s0 + mini, micro_seqs)] for s0 in range(0, local, mini)]
+    lens = x["lens"].cpu()
+    tlen = x["mask"].shape[1]
+    counts = None if bool((lens == tlen).all()) else {(sl.start, sl.stop): int(lens[sl].sum()) for mbs in plan for sl in mbs}
+    return plan, counts
 
 
 # ------------------------------------------------------------------------------------------------------------------
-# one step, inputs in pinned host memory (end to end through the public API)
+# one step end to end: the rollout batch lives in pinned host memory
 # ------------------------------------------------------------------------------------------------------------------
-class HostFeed:
-    """Pinned host copies of this rank's inputs and two device staging sets; copies run on their own stream."""
+class HostBatch:
+    """Pinned host copies of this rank's inputs (what the driver process hands a worker in the reference: a DataProto of
+    CPU tensors, moved by ``data.to("cuda")`` in fsdp_workers.py)."""
 
-    KEYS = ("hidden", "labels", "old", "ref", "mask", "adv")
-
-    def __init__(self, x, adv, plan, dev):
-        self.dev = dev
-        self.host = {}
-        for k in self.KEYS:
-            src = adv if k == "adv" else x[k]
-            buf = torch.empty(src.shape, dtype=src.dtype, pin_memory=True)
-            buf.copy_(src)
-            self.host[k] = buf
-        self.max_mb = max(sl.stop - sl.start for mbs in plan for sl in mbs)
-        self.stage = [{k: torch.empty((self.max_mb,) + tuple(self.host[k].shape[1:]), dtype=self.host[k].dtype, device=dev)
-                       for k in self.KEYS} for _ in range(2)]
-        self.copy_stream = torch.cuda.Stream(device=dev)
-        self.ready = [torch.cuda.Event(), torch.cuda.Event()]
-        self.free = [torch.cuda.Event(), torch.cuda.Event()]
-        self.bytes_per_step = sum(self.host[k][sl].numel() * self.host[k].element_size()
-                                  for mbs in plan for sl in mbs for k in self.KEYS)
-
-    def prefetch(self, slot, sl):
-        with torch.cuda.stream(self.copy_stream):
-            self.copy_stream.wait_event(self.free[slot])
-            n = sl.stop - sl.start
-            for k in self.KEYS:
-                self.stage[slot][k][:n].copy_(self.host[k][sl], non_blocking=True)
-            self.ready[slot].record(self.copy_stream)
-
-    def get(self, slot, sl):
-        torch.cuda.current_stream(self.dev).wait_event(self.ready[slot])
-        n = sl.stop - sl.start
-        return {k: self.stage[slot][k][:n] for k in self.KEYS}
-
-    def release(self, slot):
-        self.free[slot].record(torch.cuda.current_stream(self.dev))
+    def __init__(self, x):
+        self.t = {}
+        for k in ("hidden", "labels", "old", "ref", "mask", "rewards"):
+            buf = torch.empty(x[k].shape, dtype=x[k].dtype, pin_memory=True)
+            buf.copy_(x[k])
+            self.t[k] = buf
+        self.adv = torch.empty(x["rewards"].shape, dtype=torch.float32, pin_memory=True)
+        self.rewards_dev = torch.empty_like(x["rewards"])
+        self.mask_dev = torch.empty_like(x["mask"])
 
 
-def run_step_e2e(st, x, feed, plan, dweight, temperature, want_entropy, host_metrics, counts=None):
-    from spatialthinker_b200.sharding import allreduce_mean_
-
-    flat = [(i, sl) for i, mbs in enumerate(plan) for sl in mbs]
-    feed.prefetch(0, flat[0][1])
-    metrics = []
-    for j, (i, sl) in enumerate(flat):
-        slot = j & 1
-        if j + 1 < len(flat):
-            feed.prefetch(slot ^ 1, flat[j + 1][1])
-        mb = feed.get(slot, sl)
-        res = st.grpo_micro_batch_step(mb["hidden"], x["weight"], mb["labels"], mb["old"], mb["adv"], mb["ref"], mb["mask"],
-                                       temperature=temperature, grad_accum=float(len(plan[i])), dweight_accum=dweight,
-                                       want_entropy=want_entropy, entropy_coeff=ENTROPY_COEFF,
-                                       valid_rows=None if counts is None else counts[(sl.start, sl.stop)],
-                                       defer=DEFER, **CLIP, **KL)
-        feed.release(slot)
-        metrics.append(res["metrics"])
-        if j + 1 == len(flat) or flat[j + 1][0] != i:
-            if DEFER is not None:
-                DEFER.flush()
-            allreduce_mean_(dweight)
-            metrics.append(torch.linalg.vector_norm(dweight).expand(metrics[0].shape[0]))
-            dweight.zero_()
-    host_metrics.copy_(torch.stack(metrics), non_blocking=True)  # the step's result goes back to the host
-    return host_metrics
+def run_step_e2e(st, actor, x, host, world):
+    rank = dist.get_rank() if world > 1 else 0
+    # rewards + mask host -> device, advantages on the device, back to the host batch (the reference computes them on the
+    # driver and ships them with the batch: ray_trainer.py:148-175)
+    host.rewards_dev.copy_(host.t["rewards"], non_blocking=True)
+    host.mask_dev.copy_(host.t["mask"], non_blocking=True)
+    adv, _ = st.core_algos.compute_grpo_outcome_advantage_sharded(host.rewards_dev, host.mask_dev, x["uid_np"], rank * x["local"])
+    host.adv.copy_(adv, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    data = st.TensorBatch({"hidden_states": host.t["hidden"], "responses": host.t["labels"], "response_mask": host.t["mask"],
+                           "old_log_probs": host.t["old"], "ref_log_probs": host.t["ref"], "advantages": host.adv},
+                          meta_info={"temperature": 1.0})
+    return actor.update_policy(data)  # streams every micro-batch host -> device; metrics come back as python floats
 
 
 # ------------------------------------------------------------------------------------------------------------------
-# CPU baseline: the oracle (restatement of the reference arithmetic) on the host cores
+# CPU baseline: the reference's own torch functions (baseline/_ref, the unmodified package installed by build()) on the
+# host cores; the oracle port when that install is absent
 # ------------------------------------------------------------------------------------------------------------------
-def cpu_pass(cfg, tokens, seed=0):
-    from oracle import grpo_oracle as O
+def load_reference():
+    """(VF, core_algos) of the UNMODIFIED reference from baseline/_ref, or None."""
+    ref_root = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref_root, "verl")):
+        return None
+    sys.dont_write_bytecode = True
+    if ref_root not in sys.path:
+        sys.path.insert(0, ref_root)
+    try:
+        import verl.trainer.core_algos as ca
+        import verl.utils.torch_functional as VF
+    except Exception:
+        return None
+    VF.FLAH_ATTN_CROSS_ENTROPY_LOSS_AVAILABLE = False  # the Triton kernel needs CUDA tensors; this arm runs on the host
+    return VF, ca
+
+
+def cpu_pass(cfg, tokens, seed=0, ref=None):
+    """One bounded sample of the path on the host: advantages -> lm_head -> log-probs -> loss -> backward, fp32."""
+    import torch.nn.functional as F
+
+    from oracle import grpo_oracle as O  # synthetic inputs (and the arithmetic, when the reference is not installed)
 
     hdim, vocab, _, _, n, _ = cfg
     seqs = n
@@ -266,29 +299,47 @@ def cpu_pass(cfg, tokens, seed=0):
     hid, w = O.synth_head(seqs * tlen, hdim, vocab, seed=seed)
     hid = hid.view(seqs, tlen, hdim)
     roll = O.synth_rollout(seqs, tlen, vocab, n, seed=seed)
-    old = -3.0 + 0.1 * torch.randn(seqs, tlen)
-    ref = -3.0 + 0.1 * torch.randn(seqs, tlen)
+    with torch.no_grad():  # old / ref around the policy's own log-probs, as in the GPU arm (not timed)
+        lp0, _ = O.lm_head_log_probs(hid, w, roll["responses"])
+    old, ref_lp = O.perturbed_log_probs(lp0, seed=seed + 1), O.perturbed_log_probs(lp0, seed=seed + 2)
+    mask = roll["response_mask"]
     t0 = time.perf_counter()
-    adv, _ = O.compute_grpo_outcome_advantage(roll["token_level_rewards"].clone(), roll["response_mask"], roll["uid"])
-    O.fused_loss_reference(hid, w, roll["responses"], old, adv, roll["response_mask"], ref, kl_penalty="low_var_kl",
-                           kl_coef=1e-2, grad_accum=1.0)
+    if ref is None:
+        adv, _ = O.compute_grpo_outcome_advantage(roll["token_level_rewards"].clone(), mask, roll["uid"])
+        O.fused_loss_reference(hid, w, roll["responses"], old, adv, mask, ref_lp, kl_penalty="low_var_kl", kl_coef=1e-2,
+                               grad_accum=1.0, **CLIP)
+    else:
+        VF, ca = ref
+        adv, _ = ca.compute_grpo_outcome_advantage(roll["token_level_rewards"].clone(), mask, roll["uid"])
+        h = hid.float().requires_grad_(True)
+        wf = w.float().requires_grad_(True)
+        z = F.linear(h, wf) / 1.0  # HF lm_head (nn.Linear, third party) + logits.div_(temperature), dp_actor.py:125-126
+        logp = -VF.log_probs_from_logits(z, roll["responses"])  # the CPU branch returns +CE (torch_functional.py:64)
+        pg, _, _, _ = ca.compute_policy_loss(old, logp, adv, mask, CLIP["clip_ratio_low"], CLIP["clip_ratio_high"],
+                                             CLIP["clip_ratio_dual"])
+        kl = VF.masked_mean(ca.compute_kl(logp, ref_lp, "low_var_kl"), mask)
+        ((pg + 1e-2 * kl) / 1.0).backward()  # dp_actor.py:271-278
     return seqs * tlen, time.perf_counter() - t0
 
 
 def cpu_baseline(cfg, budget_s=15.0):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    ref = load_reference()
     tokens = 512
-    n_tok, dt = cpu_pass(cfg, tokens)  # also warms the thread pool
+    cpu_pass(cfg, tokens, ref=ref)  # also warms the thread pool
     total_tok, total_t, passes = 0, 0.0, 0
     while total_t < budget_s and passes < 8:
-        n_tok, dt = cpu_pass(cfg, tokens, seed=passes + 1)
+        n_tok, dt = cpu_pass(cfg, tokens, seed=passes + 1, ref=ref)
         total_tok += n_tok
         total_t += dt
         passes += 1
-    return {"value": total_tok / total_t, "unit": "tokens/s", "cores": torch.get_num_threads(), "kind": "port",
+    what = ("verl.utils.torch_functional + verl.trainer.core_algos of the unmodified reference (baseline/_ref) around torch F.linear"
+            if ref is not None else "oracle/grpo_oracle.py (reference not installed)")
+    return {"value": total_tok / total_t, "unit": "tokens/s", "cores": torch.get_num_threads(),
+            "kind": "reference" if ref is not None else "port",
             "sample": f"{passes} passes x {tokens} response tokens ({cfg[4]} sequences) of the same head shape, fp32 torch on "
-                      f"{cores} host threads; oracle/grpo_oracle.py (reference is pure Python, nothing to compile)"}
+                      f"{cores} host threads; {what}"}
 
 
 def run_reference(args, cfg):
@@ -297,22 +348,26 @@ def run_reference(args, cfg):
         return
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    ref = load_reference()
     tokens = 512
     for _ in range(max(args.warmup, 1)):
-        cpu_pass(cfg, tokens)
+        cpu_pass(cfg, tokens, ref=ref)
     tot_tok, tot_t = 0, 0.0
     for i in range(args.steps):
-        n_tok, dt = cpu_pass(cfg, tokens, seed=i)
+        n_tok, dt = cpu_pass(cfg, tokens, seed=i, ref=ref)
         tot_tok += n_tok
         tot_t += dt
     val = tot_tok / tot_t
+    kind = "reference" if ref is not None else "port"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "tokens/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.config}: {cfg[5]}; each step = a bounded sample of {tokens} response tokens on the host"},
-        "cpu_baseline": {"value": val, "unit": "tokens/s", "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": f"{args.steps} steps x {tokens} tokens, oracle port of the reference torch path"},
+        "cpu_baseline": {"value": val, "unit": "tokens/s", "cores": torch.get_num_threads(), "kind": kind,
+                         "sample": f"{args.steps} steps x {tokens} tokens; " +
+                                   ("the unmodified reference's torch_functional / core_algos (baseline/_ref) around torch F.linear"
+                                    if ref is not None else "oracle port of the reference torch path")},
         "e2e": {"value": val, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
@@ -326,17 +381,19 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
-    ap.add_argument("--micro-seqs", type=int, default=0, help="sequences per micro-batch (0: 37888 tokens' worth)")
+    ap.add_argument("--micro-seqs", type=int, default=0,
+                    help="fixed sequences per micro-batch as in the reference (0: token-balanced micro-batches of 37888 tokens)")
     ap.add_argument("--sequences", type=int, default=0, help="override the rollout batch size (debug)")
     ap.add_argument("--entropy-coeff", type=float, default=0.0,
                     help="loss -= coeff * masked_mean(entropy): adds the per-element stash -> dlogits pass (not in the reference)")
-    ap.add_argument("--defer-dw", action="store_true",
-                    help="small micro-batches share one dW GEMM per group (fused.DeferredDW); no effect on the default plan")
+    ap.add_argument("--no-defer-dw", action="store_true", help="actor without the deferred dW GEMM for small micro-batches")
+    ap.add_argument("--direct", action="store_true", help="round-1 loop over grpo_micro_batch_step instead of the actor (A/B)")
+    ap.add_argument("--legacy-inputs", action="store_true", help="round-1 old/ref log-probs (-3 + 0.1 randn)")
+    ap.add_argument("--no-balance", action="store_true", help="ragged config: contiguous rank shards instead of token-balanced ones")
+    ap.add_argument("--no-records", action="store_true", help="skip the extra record at 4-sequence micro-batches")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
-    global ENTROPY_COEFF
-    ENTROPY_COEFF = args.entropy_coeff
     cfg = list(CONFIGS[args.config])
     if args.sequences:
         cfg[2] = args.sequences
@@ -370,10 +427,7 @@ def main():
     hdim, vocab, bsz, tlen, n, desc = cfg
     ragged = args.config == "c5"
     want_entropy = args.config == "c4"
-    micro_seqs = args.micro_seqs or max(1, 37888 // tlen)  # 37 x 1024 tokens = 4 internal chunks of 9472 rows
-    x = make_inputs(cfg, rank, world, dev, micro_seqs, ragged)
-    plan = step_plan(x["local"], micro_seqs)
-    dweight = torch.zeros(vocab, hdim, dtype=torch.float32, device=dev)
+    x = make_inputs(st, cfg, rank, world, dev, ragged, args.legacy_inputs, not args.no_balance)
     tokens_local = int(x["mask"].sum().item())
     tok = torch.tensor([tokens_local], dtype=torch.float64, device=dev)
     if world > 1:
@@ -398,12 +452,16 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    counts = valid_counts(x, plan)
-    if args.defer_dw:
-        global DEFER
-        from spatialthinker_b200.fused import DeferredDW
-        DEFER = DeferredDW(x["weight"], dweight)
-    dev_step = lambda: run_step_device(st, x, plan, dweight, world, 1.0, want_entropy, counts)  # noqa: E731
+    actor = st.DataParallelPPOActor(actor_config(st, x["local"], args.micro_seqs, want_entropy, args.entropy_coeff),
+                                    x["weight"], defer_dw=not args.no_defer_dw)
+    if args.direct:
+        micro = args.micro_seqs or max(1, MAX_TOKENS // tlen)
+        plan, counts = direct_plan(x, micro)
+        dweight = torch.zeros(vocab, hdim, dtype=torch.float32, device=dev)
+        dev_step = lambda: run_step_direct(st, x, plan, dweight, world, want_entropy, args.entropy_coeff, counts)  # noqa: E731
+    else:
+        seen = {}
+        dev_step = lambda: seen.update(m=run_step_device(st, actor, x, world))  # noqa: E731
     for _ in range(args.warmup):
         dev_step()
     sampler = ClockSampler(local_rank)
@@ -421,21 +479,37 @@ def main():
     lib.grpo_profile_enable(0)
     ms_per_step = ms_total / args.steps
     value = tokens_total / (ms_per_step * 1e-3)
+    n_micro = None if args.direct else len(seen["m"]["actor/pg_loss"])
+
+    # ---- the reference's shipped micro-batch size (4 sequences) with the deferred dW GEMM, a few steps
+    records = []
+    if not args.no_records and not args.direct and not args.micro_seqs and (x["local"] // OPT_STEPS) % 4 == 0:
+        actor4 = st.DataParallelPPOActor(actor_config(st, x["local"], 4, want_entropy, args.entropy_coeff), x["weight"],
+                                         defer_dw=True)
+        step4 = lambda: run_step_device(st, actor4, x, world)  # noqa: E731
+        step4()
+        k = max(2, args.steps // 10)
+        ms4 = timed(step4, k) / k
+        records.append({"name": "reference micro-batch size", "micro_batch_sequences": 4, "defer_dw": True, "via": "DataParallelPPOActor.update_policy",
+                        "steps": k, "warmup": 1, "ms_per_step": ms4, "value": tokens_total / (ms4 * 1e-3), "unit": "tokens/s",
+                        "vs_default": ms_per_step / ms4})
+        actor4.release_workspaces()
+        del actor4
 
     # ---- end to end from pinned host memory
     e2e = None
-    if not args.no_e2e:
-        local_scores = x["rewards"].sum(-1)
-        adv = (local_scores - local_scores.mean())[:, None] * x["mask"]  # any advantage values: same work
-        feed = HostFeed(x, adv, plan, dev)
-        n_rows = sum(len(m) for m in plan) + len(plan)
-        host_metrics = torch.empty(n_rows, _lib.NUM_METRICS, dtype=torch.float32).pin_memory()
-        e2e_step = lambda: run_step_e2e(st, x, feed, plan, dweight, 1.0, want_entropy, host_metrics, counts)  # noqa: E731
+    if not args.no_e2e and not args.direct:
+        host = HostBatch(x)
+        e2e_step = lambda: run_step_e2e(st, actor, x, host, world)  # noqa: E731
         for _ in range(min(args.warmup, 1)):
             e2e_step()
+        h2d0 = actor._stager.h2d_bytes
         ms_e2e = timed(e2e_step, args.steps) / args.steps
-        e2e = {"value": tokens_total / (ms_e2e * 1e-3), "unit": "tokens/s", "h2d_bytes_per_step": int(feed.bytes_per_step * world),
-               "d2h_bytes_per_step": int(host_metrics.numel() * 4 * world), "ms_per_step": ms_e2e}
+        h2d = (actor._stager.h2d_bytes - h2d0) // args.steps + host.t["rewards"].numel() * 4 + host.t["mask"].numel() * 8
+        d2h = host.adv.numel() * 4 + (n_micro or 0) * _lib.NUM_METRICS * 4 + OPT_STEPS * 4
+        e2e = {"value": tokens_total / (ms_e2e * 1e-3), "unit": "tokens/s", "h2d_bytes_per_step": int(h2d * world),
+               "d2h_bytes_per_step": int(d2h * world), "ms_per_step": ms_e2e,
+               "via": "DataParallelPPOActor.update_policy on a pinned-host batch (advantage kernels and their D2H included)"}
 
     if rank != 0:
         if world > 1:
@@ -458,18 +532,29 @@ def main():
         t = json.load(open(tpath)).get(dom["name"])
         if t:
             traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
+    gemm_ms = sum(k["total_ms"] for k in gemms) / args.steps
     roofline = {"bound": "tensor", "kernel": dom["name"], "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak, "peak_kind": f"{peaks['src']} sustained bf16 (burst {peaks['burst']})",
                 "traffic": traffic, "algorithmic_flops_per_launch": 2.0 * hdim * vocab * rows_per_launch, "kernels": kernels,
+                "ms_per_step_outside_phase_timers": ms_per_step - sum(k["total_ms"] for k in kernels) / args.steps,
+                "gemm_ms_per_step": gemm_ms,
                 "whole_step_tflops_algorithmic": 6.0 * hdim * vocab * tokens_total / (ms_per_step * 1e-3) / 1e12 / world}
+    micro_desc = (f"{args.micro_seqs} sequences" if args.micro_seqs else
+                  f"token-balanced, <= {MAX_TOKENS} tokens ({n_micro} micro-batches per step)" if not args.direct else
+                  f"{max(1, MAX_TOKENS // tlen)} sequences (direct loop)")
     out = {
         "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
         "config": {"workload": f"{args.config}: {desc}", "hidden": hdim, "vocab": vocab, "sequences": bsz, "response_len": tlen,
-                   "group_n": n, "micro_batch_sequences": micro_seqs, "optimizer_steps_per_step": len(plan), "defer_dw": bool(args.defer_dw),
-                   "loss": "GRPO clip .2/.3/3.0 + low_var_kl 1e-2" + (f" - {args.entropy_coeff} * entropy" if args.entropy_coeff else ""), "l2": "inputs (>= 30 GB) far exceed the 126 MB L2",
-                   "parallelism": f"dp{world} by sequence, dW mean all-reduce (NCCL)"},
+                   "group_n": n, "via": "grpo_micro_batch_step loop" if args.direct else "DataParallelPPOActor.update_policy",
+                   "micro_batch": micro_desc, "optimizer_steps_per_step": OPT_STEPS, "defer_dw": not args.no_defer_dw,
+                   "inputs": "round-1 (-3 + 0.1 randn)" if args.legacy_inputs else "SURVEY 8(d): old/ref = logp + 0.1 randn, 1% +-1.5 outliers",
+                   "loss": "GRPO clip .2/.3/3.0 + low_var_kl 1e-2" + (f" - {args.entropy_coeff} * entropy" if args.entropy_coeff else ""),
+                   "l2": "inputs (>= 30 GB) far exceed the 126 MB L2",
+                   "parallelism": f"dp{world} by sequence" + (", token-balanced rank shards (Karmarkar-Karp)" if ragged and not args.no_balance else "") + ", dW mean all-reduce (NCCL)",
+                   "tokens_per_rank": x["tokens_per_rank"], "tokens_per_rank_unbalanced": x["tokens_per_rank_unbalanced"],
+                   "records": records},
         "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline, "e2e": e2e,
     }
     if not args.no_cpu:

@@ -49,7 +49,11 @@ typedef struct CUstream_st* grpo_stream_t;
 #define GRPO_MET_SCALED 7      /* total / grad_accum, the back-propagated scalar  dp_actor.py:277   */
 #define GRPO_MET_TRUE_ENTROPY 8 /* masked_mean(lse - sum p z) when entropy was requested, else 0      */
 #define GRPO_MET_MASK_SUM 9     /* sum(mask): valid tokens of the micro-batch                        */
-#define GRPO_NUM_METRICS 10
+#define GRPO_MET_SATURATED 10   /* unmasked tokens with log p <= -69.3 (= -100 ln 2): the fused head references its
+                                 * softmax to the label's own logit and clamps exp2 arguments at 100, so the row sum of
+                                 * such a token may be saturated; 0 for anything a policy could have sampled. The
+                                 * reference (max-subtracted cross-entropy, torch_functional.py:45-66) has no such limit. */
+#define GRPO_NUM_METRICS 11
 
 int grpo_abi_version(void);
 const char* grpo_last_error(void);
@@ -64,7 +68,8 @@ long long grpo_launch_count(void);
 /* Tuning knobs for experiments (process-wide): "cta_group" 1|2, "fwd_panel" row blocks, "sync_fwd" / "sync_dh" /
  * "sync_dw" progress-barrier periods in K-blocks (0 = off), "l2_hints" 0|1, "dw_split" 0|1|2 (split-K tail of the dW GEMM;
  * 2 = the multi-round plan), "dh_split" 0|1 (dHidden GEMM: fp32 split-K path when its tiles are not a whole number of
- * rounds). Defaults are the measured configuration. */
+ * rounds), "deterministic" 0|1 (run-to-run bit-reproducible gradients: no split-K, the one-hot rows of dW summed in row
+ * order instead of with atomics). Defaults are the measured configuration. */
 int grpo_set_option(const char* name, int value);
 /* Measurement aid: with option "clk_probe" = 1 the three GEMM kernels of the chunk pipeline write
  * 1024 x uint64 each (order logits / dHidden / dW) at this byte offset of the caller's workspace:
@@ -147,9 +152,24 @@ int grpo_deferred_dw_flush(int64_t total_rows, int64_t capacity_rows, int64_t hi
                            void* workspace, size_t workspace_bytes, grpo_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * Per-optimizer-step passes over the fp32 weight-gradient accumulator (the head's share of _optimizer_step,
+ * dp_actor.py:155-167: clip_grad_norm_ + zero_grad). HBM-bound, one pass each.
+ *   grpo_grad_sumsq     : out[0] (+)= sum(grad^2) in fp64, partial sums reduced in a fixed order; zero_after != 0 writes
+ *                         zeros back in the same pass; accumulate != 0 adds to out[0] (global norm over several tensors).
+ *                         scratch: GRPO_GRAD_SCRATCH_DOUBLES doubles of device memory.
+ *   grpo_grad_scale_cast: out_bf16[i] = bf16(grad[i] * scale), scale = scale_dev[0] (device, e.g. the clip coefficient)
+ *                         when non-null else scale_host; zero_after != 0 zeroes grad in the same pass.
+ * ------------------------------------------------------------------------------------------------------------------ */
+#define GRPO_GRAD_SCRATCH_DOUBLES 1024
+int grpo_grad_sumsq(float* grad, int64_t n, int zero_after, int accumulate, double* out, double* scratch,
+                    grpo_stream_t stream);
+int grpo_grad_scale_cast(float* grad, int64_t n, const float* scale_dev, float scale_host, void* out_bf16,
+                         int zero_after, grpo_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Token-level policy loss on given log-probs (no lm_head): the four masked means of compute_policy_loss
  * (core_algos.py:291-353), optionally the KL term (compute_kl :394-436) and dL/dlogp with
- * L = (pg + kl_coef * kl) / grad_accum.   acc_scratch: 8 doubles of device scratch.
+ * L = (pg + kl_coef * kl) / grad_accum.   acc_scratch: 16 doubles of device scratch.
  * ------------------------------------------------------------------------------------------------------------------ */
 int grpo_policy_loss_fwd_bwd(const float* logp, const float* old_logp, const float* advantages, const float* ref_logp,
                              const void* mask, int mask_dtype, int64_t n, float clip_ratio_low, float clip_ratio_high,

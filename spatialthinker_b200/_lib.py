@@ -19,11 +19,13 @@ LIB_PATH = os.environ.get("GRPO_B200_LIB") or os.path.join(_HERE, "libgrpo_b200.
 KL_MODES = {None: -1, "none": -1, "low_var_kl": 0, "kl": 1, "abs": 2, "mse": 3, "chi2": 4}
 MASK_F32, MASK_I64, MASK_U8, MASK_NONE = 0, 1, 2, 3
 LOGITS_F32, LOGITS_BF16, LOGITS_F16 = 0, 1, 2
-NUM_METRICS = 10
+NUM_METRICS = 11
 NUM_PHASES = 6
 PHASE_NAMES = ("logits_gemm", "row_stats", "token_loss", "grad_prep", "dhidden_gemm", "dweight_gemm")
 MET_PG_LOSS, MET_CLIPFRAC_HI, MET_CLIPFRAC_LO, MET_PPO_KL, MET_KL_LOSS = 0, 1, 2, 3, 4
-MET_ENTROPY, MET_TOTAL, MET_SCALED, MET_TRUE_ENTROPY, MET_MASK_SUM = 5, 6, 7, 8, 9
+MET_ENTROPY, MET_TOTAL, MET_SCALED, MET_TRUE_ENTROPY, MET_MASK_SUM, MET_SATURATED = 5, 6, 7, 8, 9, 10
+GRAD_SCRATCH_DOUBLES = 1024
+ABI_VERSION = 2
 
 _P = c_void_p
 _SIGNATURES = {
@@ -51,6 +53,8 @@ _SIGNATURES = {
          c_float, c_float, _P, _P, _P, _P, _P, c_int64, c_int64, _P, c_size_t, _P],
     ),
     "grpo_deferred_dw_flush": (c_int, [c_int64, c_int64, c_int64, c_int64, _P, _P, c_size_t, _P]),
+    "grpo_grad_sumsq": (c_int, [_P, c_int64, c_int, c_int, _P, _P, _P]),
+    "grpo_grad_scale_cast": (c_int, [_P, c_int64, _P, c_float, _P, c_int, _P]),
     "grpo_policy_loss_fwd_bwd": (
         c_int,
         [_P, _P, _P, _P, _P, c_int, c_int64, c_float, c_float, c_float, c_int, c_float, c_float, _P, _P, _P, _P],

@@ -146,7 +146,7 @@ class _PolicyLoss(torch.autograd.Function):
         n = lp.numel()
         dlogp = torch.empty(n, dtype=torch.float32, device=dev)
         metrics = torch.empty(_lib.NUM_METRICS, dtype=torch.float32, device=dev)
-        acc = torch.empty(8, dtype=torch.float64, device=dev)
+        acc = torch.empty(16, dtype=torch.float64, device=dev)
         with torch.cuda.device(dev):
             _lib.check(
                 lib.grpo_policy_loss_fwd_bwd(lp.data_ptr(), old.data_ptr(), adv.data_ptr(), None, mask.data_ptr(), code,

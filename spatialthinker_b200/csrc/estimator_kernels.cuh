@@ -174,8 +174,8 @@ __global__ void masked_var_finalize_kernel(const double* __restrict__ acc, int u
   }
 }
 // out = (x - mean) * rsqrt(var + eps)   (torch_functional.py:92-95; every position, masked or not, as the reference)
-__global__ void whiten_apply_kernel(const float* __restrict__ x, size_t n, const double* __restrict__ acc, float eps,
-                                    float* __restrict__ out) {
+// x and out may alias (grpo_gae_advantage / grpo_masked_whiten whiten in place): no __restrict__ on them.
+__global__ void whiten_apply_kernel(const float* x, size_t n, const double* __restrict__ acc, float eps, float* out) {
   const float mean = whiten_mean(acc, 1e-8f);
   const float scale = __fdiv_rn(1.f, __fsqrt_rn(whiten_var(acc, 1) + eps));
   batched_grid_stride<2 * kEwBatch>(

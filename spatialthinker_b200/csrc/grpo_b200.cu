@@ -15,6 +15,7 @@
 #include "compact_kernels.cuh"
 #include "estimator_kernels.cuh"
 #include "gemm_core.cuh"
+#include "grad_kernels.cuh"
 #include "lmhead_kernels.cuh"
 #include "logits_kernels.cuh"
 #include "loss_kernels.cuh"
@@ -208,6 +209,10 @@ struct Knobs {
   // convert in a fix-up pass (chunk_backward). 0: always the direct bf16 epilogue. Measured on B200
   // (profiles/r1_ab_dh_split.log): dHidden GEMM 3.93 -> 3.16 ms at 4096 rows, 1.68 -> 0.76 ms at 1024 rows.
   int dh_split = 1;
+  // Run-to-run bit-reproducible gradients: no split-K (dw_split / dh_split are ignored: the K slices of a tile add into
+  // the same fp32 words in completion order) and the one-hot rows of dW summed in row order instead of with atomics
+  // (grad_kernels.cuh). Costs ~1 % (profiles/); off by default.
+  int deterministic = 0;
 };
 static Knobs g_knobs;
 static std::once_flag g_knobs_once;
@@ -235,6 +240,7 @@ static void init_knobs() {
     g_knobs.dh_split = env_int("GRPO_DH_SPLIT", g_knobs.dh_split) != 0;
     g_knobs.acc_lead = env_int("GRPO_ACC_LEAD", g_knobs.acc_lead);
     g_knobs.st_hint = env_int("GRPO_ST_HINT", g_knobs.st_hint) & 3;
+    g_knobs.deterministic = env_int("GRPO_DETERMINISTIC", g_knobs.deterministic) != 0;
   });
 }
 
@@ -254,6 +260,7 @@ static int get_dev(DevInfo* out) {
     sms_cache[dev] = p.multiProcessorCount;
   }
   static_cast<Knobs&>(*out) = g_knobs;
+  if (out->deterministic) out->dw_split = out->dh_split = 0;
   out->sms = sms_cache[dev];
   return 0;
 }
@@ -407,6 +414,7 @@ struct Workspace {
   float *part_sum = nullptr, *part_ez = nullptr;  // [n_tiles][rows_pad]
   float *a_label = nullptr, *lse = nullptr, *inv_sum = nullptr, *dlogp = nullptr, *dent = nullptr, *ent = nullptr;
   float *row_scale = nullptr, *onehot = nullptr;
+  int32_t *oh_next = nullptr, *oh_has_prev = nullptr;  // per-label row chains of the deterministic one-hot pass
   double* acc = nullptr;
   uint32_t* sync = nullptr;  // progress-barrier counters, one per GEMM of the chunk pipeline (first 64 bytes)
   unsigned long long* probe = nullptr;  // clock probes of the three GEMMs, 1024 x u64 each (measurement aid)
@@ -449,6 +457,8 @@ static Workspace carve(void* base, int64_t rows, int64_t hdim, int64_t vocab, bo
   w.ent = reinterpret_cast<float*>(take(vec));
   w.row_scale = reinterpret_cast<float*>(take(vec));
   w.onehot = reinterpret_cast<float*>(take(vec));
+  w.oh_next = reinterpret_cast<int32_t*>(take(vec));
+  w.oh_has_prev = reinterpret_cast<int32_t*>(take(vec));
   w.acc = reinterpret_cast<double*>(take(ACC_N * sizeof(double)));
   w.probe_offset = off + 64;
   w.sync = reinterpret_cast<uint32_t*>(take(64 + 3 * 8192));
@@ -476,6 +486,8 @@ static Workspace slot_view(const Workspace& w, int64_t row0, int64_t hdim) {
   v.ent = w.ent + row0;
   v.row_scale = w.row_scale + row0;
   v.onehot = w.onehot + row0;
+  v.oh_next = w.oh_next + row0;
+  v.oh_has_prev = w.oh_has_prev + row0;
   return v;
 }
 
@@ -607,7 +619,14 @@ static int chunk_backward(const DevInfo& dev, const Workspace& w, const __nv_bfl
     if (factorised) {
       scale_scatter_kernel<<<cdiv(n * 32, 256), 256, 0, stream>>>(hidden + r0 * h, labels + r0, dlogp, w.inv_sum,
                                                                   1.f / temperature, un, uh, uv, w.row_scale, w.onehot,
-                                                                  w.hd_scaled, dweight);
+                                                                  w.hd_scaled, dev.deterministic ? nullptr : dweight);
+      if (dev.deterministic) {  // the one-hot rows of dW in row order instead of with atomics
+        GRPO_CUDA(cudaMemsetAsync(w.oh_has_prev, 0, static_cast<size_t>(n) * sizeof(int32_t), stream));
+        onehot_links_kernel<<<cdiv(n * 32, 256), 256, 0, stream>>>(labels + r0, un, uv, w.oh_next, w.oh_has_prev);
+        onehot_ordered_kernel<<<cdiv(n * 32, 256), 256, 0, stream>>>(hidden + r0 * h, labels + r0, w.onehot, w.oh_next,
+                                                                     w.oh_has_prev, un, uh, uv, dweight);
+        count_launch(2);
+      }
     } else {
       dim3 grid(cdiv(cdiv(v, 64), kDlogitsColBlocksPerCta), cdiv(n, 64));  // (runs of column blocks, row blocks)
       stash_to_dlogits_kernel<<<grid, 256, 0, stream>>>(w.stash, static_cast<uint32_t>(w.stash_vb), un, uv, w.inv_sum,
@@ -706,7 +725,7 @@ using namespace grpo;
 // ============================================================================================ C ABI
 extern "C" {
 
-int grpo_abi_version(void) { return 1; }
+int grpo_abi_version(void) { return 2; }
 const char* grpo_last_error(void) { return g_err; }
 long long grpo_launch_count(void) { return g_launches.load(); }
 
@@ -730,6 +749,7 @@ int grpo_set_option(const char* name, int value) {
   else if (!strcmp(name, "dw_split")) g_knobs.dw_split = value < 0 ? 0 : (value > 2 ? 2 : value);  // 2: grpo_debug_gemm runs the multi-round plan
   else if (!strcmp(name, "epi_share")) g_knobs.epi_share = value != 0;
   else if (!strcmp(name, "dh_split")) g_knobs.dh_split = value != 0;
+  else if (!strcmp(name, "deterministic")) g_knobs.deterministic = value != 0;
   else if (!strcmp(name, "chunk_rows")) g_knobs.chunk_rows = value > 0 ? (value + 511) / 512 * 512 : 0;
   else return fail(GRPO_ERR_ARG, "unknown option '%s'", name);
   return 0;
@@ -976,6 +996,32 @@ int grpo_deferred_dw_flush(int64_t total_rows, int64_t capacity_rows, int64_t hi
   Workspace w;
   GRPO_TRY(carve_deferred(&w, workspace, workspace_bytes, capacity_rows, hidden_dim, vocab));
   return dw_gemm(dev, w, w.hd_scaled, total_rows, hidden_dim, vocab, dweight, stream);
+}
+
+int grpo_grad_sumsq(float* grad, int64_t n, int zero_after, int accumulate, double* out, double* scratch,
+                    grpo_stream_t stream) {
+  if (!grad || !out || !scratch) return fail(GRPO_ERR_ARG, "grad / out / scratch must not be null");
+  if (n < 0) return fail(GRPO_ERR_ARG, "negative length");
+  if (reinterpret_cast<uintptr_t>(grad) & 15u) return fail(GRPO_ERR_ARG, "grad must be 16-byte aligned");
+  grad_sumsq_kernel<<<kGradBlocks, kGradThreads, 0, stream>>>(grad, static_cast<size_t>(n), zero_after, scratch);
+  grad_sumsq_finalize_kernel<<<1, 32, 0, stream>>>(scratch, kGradBlocks, accumulate, out);
+  count_launch(2);
+  GRPO_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int grpo_grad_scale_cast(float* grad, int64_t n, const float* scale_dev, float scale_host, void* out_bf16,
+                         int zero_after, grpo_stream_t stream) {
+  if (!grad || !out_bf16) return fail(GRPO_ERR_ARG, "grad / out must not be null");
+  if (n < 0) return fail(GRPO_ERR_ARG, "negative length");
+  if ((reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(out_bf16)) & 15u)
+    return fail(GRPO_ERR_ARG, "grad / out must be 16-byte aligned");
+  if (n == 0) return 0;
+  grad_scale_cast_kernel<<<kGradBlocks * 2, kGradThreads, 0, stream>>>(grad, static_cast<size_t>(n), scale_dev, scale_host,
+                                                                       static_cast<__nv_bfloat16*>(out_bf16), zero_after);
+  count_launch();
+  GRPO_CUDA(cudaGetLastError());
+  return 0;
 }
 
 int grpo_policy_loss_fwd_bwd(const float* logp, const float* old_logp, const float* advantages, const float* ref_logp,

@@ -24,7 +24,10 @@ struct LossCfg {
 };
 
 // accumulator slots (double)
-enum { ACC_MASK = 0, ACC_PG = 1, ACC_CF_HI = 2, ACC_CF_LO = 3, ACC_NEG_X = 4, ACC_KL = 5, ACC_LOGP = 6, ACC_ENT = 7, ACC_N = 8 };
+enum { ACC_MASK = 0, ACC_PG = 1, ACC_CF_HI = 2, ACC_CF_LO = 3, ACC_NEG_X = 4, ACC_KL = 5, ACC_LOGP = 6, ACC_ENT = 7, ACC_SAT = 8, ACC_N = 9 };
+// log p at or below which the fused head's exp2 clamp (kClampLog2 = 100 in lmhead_kernels.cuh) may have bound: a clamped
+// element contributes exactly 2^100 to the row sum, so sum >= 2^100 <=> log p[label] <= -100 ln 2
+constexpr float kSaturatedLogp = -69.3f;
 // metric slots (float) written by loss_finalize_kernel
 enum {
   MET_PG_LOSS = 0,      // masked_mean(policy loss)                      (core_algos.py:349)
@@ -37,7 +40,8 @@ enum {
   MET_SCALED = 7,       // total / grad_accum - the value that is back-propagated (dp_actor.py:277)
   MET_TRUE_ENTROPY = 8, // masked_mean(lse - sum p z) when the per-token entropy was requested, else 0
   MET_MASK_SUM = 9,     // sum(mask): the micro-batch's valid-token count
-  MET_N = 10
+  MET_SATURATED = 10,   // number of unmasked tokens with log p <= -69.3: the fused head's lse may be saturated there
+  MET_N = 11
 };
 
 __device__ __forceinline__ float load_mask(const void* m, int dtype, size_t i) {
@@ -175,7 +179,7 @@ __global__ void token_loss_kernel(const float* __restrict__ logp, const float* _
                                   float* __restrict__ dent_out) {
   const float denom = static_cast<float>(acc[ACC_MASK]) + 1e-8f;
   const float wnorm = cfg.inv_grad_accum / denom;
-  float v[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   struct In {
     float m, lp, old, adv, ref, ent;
   };
@@ -206,12 +210,13 @@ __global__ void token_loss_kernel(const float* __restrict__ logp, const float* _
           v[4] += klv * m;
           v[5] += lp * m;
           if (entropy) v[6] += in.ent * m;
+          if (lp <= kSaturatedLogp) v[7] += 1.f;
         }
         if (dlogp_out) dlogp_out[i] = (m != 0.f) ? m * wnorm * (dpg + cfg.kl_coef * dkl) : 0.f;
         if (dent_out) dent_out[i] = (m != 0.f) ? -cfg.entropy_coef * m * wnorm : 0.f;
       });
-  const int slot[7] = {ACC_PG, ACC_CF_HI, ACC_CF_LO, ACC_NEG_X, ACC_KL, ACC_LOGP, ACC_ENT};
-  block_accumulate<7>(v, acc, slot);
+  const int slot[8] = {ACC_PG, ACC_CF_HI, ACC_CF_LO, ACC_NEG_X, ACC_KL, ACC_LOGP, ACC_ENT, ACC_SAT};
+  block_accumulate<8>(v, acc, slot);
 }
 
 __global__ void loss_finalize_kernel(const double* __restrict__ acc, LossCfg cfg, float* __restrict__ metrics) {
@@ -232,6 +237,7 @@ __global__ void loss_finalize_kernel(const double* __restrict__ acc, LossCfg cfg
   metrics[MET_SCALED] = total * cfg.inv_grad_accum;
   metrics[MET_TRUE_ENTROPY] = ent;
   metrics[MET_MASK_SUM] = static_cast<float>(acc[ACC_MASK]);
+  metrics[MET_SATURATED] = static_cast<float>(acc[ACC_SAT]);
 }
 
 // Elementwise KL estimator with its derivative (standalone compute_kl surface).

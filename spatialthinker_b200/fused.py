@@ -125,11 +125,13 @@ class DeferredDW:
         self.device = dev
         self.dweight = dweight_accum
         self.vocab, self.hdim = weight.shape
-        self.capacity = int(lib.grpo_chunk_capacity_rows())
-        self.nbytes = int(lib.grpo_fused_loss_workspace_bytes(self.capacity, self.hdim, self.vocab))
-        # its own buffer: the stash must survive other head calls (compute_log_prob ...) between two micro-batches
-        # (zeroed once: stash rows no launch has written yet meet zero operand rows in the dW GEMM and must be finite)
-        self.workspace = torch.zeros(self.nbytes, dtype=torch.uint8, device=dev)
+        # whole 512-row tiles only (the chunk_rows knob may have been set to anything); 0 disables deferral
+        self.capacity = int(lib.grpo_chunk_capacity_rows()) // 512 * 512
+        self.nbytes = int(lib.grpo_fused_loss_workspace_bytes(self.capacity, self.hdim, self.vocab)) if self.capacity else 0
+        # its own buffer: the stash must survive other head calls (compute_log_prob ...) between two micro-batches.
+        # Allocated by the first reserve() that succeeds - an actor whose micro-batches all exceed the capacity never
+        # pays for it.
+        self.workspace: Optional[torch.Tensor] = None
         self.next_row0 = 0   # where the next slot starts (multiple of 512)
         self.total_rows = 0  # end of the last slot
         self.pending = 0     # micro-batches collected since the last flush
@@ -139,6 +141,9 @@ class DeferredDW:
         never fit and the caller should take the ordinary path."""
         if rows <= 0 or rows > self.capacity:
             return None
+        if self.workspace is None:
+            # zeroed once: stash rows no launch has written yet meet zero operand rows in the dW GEMM and must be finite
+            self.workspace = torch.zeros(self.nbytes, dtype=torch.uint8, device=self.device)
         if self.next_row0 + rows > self.capacity:
             self.flush()
         row0 = self.next_row0
@@ -158,6 +163,11 @@ class DeferredDW:
                     "grpo_deferred_dw_flush",
                 )
         self.next_row0 = self.total_rows = self.pending = 0
+
+    def release(self) -> None:
+        """Flush what is pending and give the chunk workspace back (it is re-allocated by the next small micro-batch)."""
+        self.flush()
+        self.workspace = None
 
 
 # ----------------------------------------------------------------------------------------------------------------

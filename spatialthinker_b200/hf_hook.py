@@ -105,3 +105,96 @@ def make_hidden_fn(model: torch.nn.Module) -> Callable[[Dict[str, Any]], torch.T
                                       micro["responses"].size(-1), **extra).to(torch.bfloat16)
 
     return hidden_fn
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# forward patch: the model returns .log_probs instead of .logits
+# ----------------------------------------------------------------------------------------------------------------
+class FusedHeadOutput:
+    """What a patched ``forward`` returns when it is given ``responses``: per-token log-probs of the response tokens
+    (and optionally their entropy, or the fused GRPO loss) instead of ``[bsz, seqlen, vocab]`` logits."""
+
+    __slots__ = ("log_probs", "entropy", "loss", "metrics", "logits", "last_hidden_state")
+
+    def __init__(self, log_probs, entropy=None, loss=None, metrics=None, last_hidden_state=None):
+        self.log_probs, self.entropy, self.loss, self.metrics = log_probs, entropy, loss, metrics
+        self.logits = None  # never materialised
+        self.last_hidden_state = last_hidden_state
+
+
+_PATCH_ATTR = "_grpo_b200_original_forward"
+
+
+def patch_model(model: torch.nn.Module) -> torch.nn.Module:
+    """Swap ``model.forward`` (``Qwen2_5_VLForConditionalGeneration``, ``Qwen2VLForConditionalGeneration``,
+    ``Qwen2ForCausalLM`` and any other ``*ForCausalLM`` whose body is ``model.model`` and whose head is a bias-free
+    ``lm_head``) for one that can return log-probs. The sibling of the reference's attention patch
+    (verl/models/monkey_patch.py:22-32); the call site it serves is ``_forward_micro_batch`` (dp_actor.py:64-153).
+
+    The patched forward behaves exactly like the original unless it is called with ``responses=`` (``[bsz, T]`` int64):
+    then it runs the transformer body only, keeps the ``T`` hidden rows per sequence that predict the response tokens
+    (``hidden[:, -T-1:-1]``, dp_actor.py:150; or, with ``padding_free_mask=attention_mask``, the same rows out of the
+    packed ``[1, total_nnz, H]`` stream of the padding-free branch, dp_actor.py:118-139) and feeds them to the fused head
+    together with ``self.lm_head.weight``. Extra keyword arguments:
+
+    * ``temperature`` (float, default 1.0), ``want_entropy`` (bool) -> ``out.log_probs`` / ``out.entropy`` ``[bsz, T]``,
+      differentiable (autograd into the body and into ``lm_head.weight``; the backward recomputes the logits tiles);
+    * ``grpo=dict(old_log_probs=, advantages=, response_mask=, ref_log_probs=None, clip_ratio_low=, ..., kl_penalty=,
+      kl_coef=, grad_accum=)`` -> additionally ``out.loss`` (scalar to call ``.backward()`` on; the gradients are produced
+      in the forward pass, three GEMM units in total) and ``out.metrics`` (the ``actor/*`` scalars, on the device).
+
+    FSDP: the head runs INSIDE the wrapped module's forward, i.e. while the root FSDP unit - which owns ``embed_tokens``,
+    the final norm and ``lm_head`` under the reference's wrap policy (fsdp_workers.py:242-280) - has its flat parameter
+    all-gathered, so ``self.lm_head.weight`` is the full ``[V, H]`` view; its gradient flows back through autograd into
+    the flat parameter and is reduce-scattered by FSDP like any other (a weight tied to ``embed_tokens``, as on the 3B
+    checkpoints, simply receives both contributions). Nothing needs ``summon_full_params``.
+    """
+    if getattr(model, _PATCH_ATTR, None) is not None:
+        return model
+    transformer_body(model)  # raises for unsupported architectures
+    lm_head_weight(model)
+    original = model.forward
+
+    def forward(*args, responses=None, temperature: float = 1.0, want_entropy: bool = False, grpo=None,
+                padding_free_mask=None, **kwargs):
+        if responses is None:
+            return original(*args, **kwargs)
+        from .fused import fused_grpo_loss, fused_lm_head_log_probs
+
+        kwargs.pop("labels", None)
+        kwargs.setdefault("use_cache", False)
+        out = transformer_body(model)(*args, **kwargs)
+        hidden = out.last_hidden_state if hasattr(out, "last_hidden_state") else out[0]
+        t_len = responses.size(-1)
+        if padding_free_mask is not None:
+            rows = packed_response_hidden_states(hidden, padding_free_mask, t_len)
+        else:
+            rows = hidden[:, -t_len - 1: -1]
+        rows = rows.to(torch.bfloat16)
+        weight = lm_head_weight(model)
+        if weight.dtype != torch.bfloat16:
+            weight = weight.to(torch.bfloat16)  # differentiable cast (fp32 master weights)
+        if grpo is None:
+            logp, ent = fused_lm_head_log_probs(rows, weight, responses, temperature, want_entropy)
+            return FusedHeadOutput(logp, ent, last_hidden_state=hidden)
+        g = dict(grpo)
+        loss, metrics = fused_grpo_loss(rows, weight, responses, g.pop("old_log_probs"), g.pop("advantages"),
+                                        g.pop("ref_log_probs", None), g.pop("response_mask"), temperature=temperature,
+                                        want_entropy=want_entropy, **g)
+        return FusedHeadOutput(metrics.pop("log_probs"), metrics.pop("entropy", None), loss, metrics, hidden)
+
+    setattr(model, _PATCH_ATTR, original)
+    model.forward = forward
+    return model
+
+
+def unpatch_model(model: torch.nn.Module) -> torch.nn.Module:
+    """Undo :func:`patch_model`."""
+    original = getattr(model, _PATCH_ATTR, None)
+    if original is None:
+        return model
+    model.__dict__.pop("forward", None)  # the patched function lives in the instance dict
+    if getattr(original, "__func__", None) is not type(model).forward:  # forward had already been overridden per instance
+        model.forward = original
+    delattr(model, _PATCH_ATTR)
+    return model

@@ -51,6 +51,13 @@ class TensorBatch:
     def split(self, split_size: int) -> List["TensorBatch"]:
         return self.chunk(len(self) // split_size)
 
+    def take(self, index: Sequence[int]) -> "TensorBatch":
+        """Rows ``index`` in that order (what ``torch.cat([batch[i:i+1] for i in partition])`` builds in the reference's
+        ``rearrange_micro_batches``, seqlen_balancing.py:245-251)."""
+        idx = torch.as_tensor(list(index), dtype=torch.long)
+        batch = {k: v.index_select(0, idx.to(v.device)) for k, v in self.batch.items()}
+        return TensorBatch(batch, {k: v[idx.numpy()] for k, v in self.non_tensor_batch.items()}, self.meta_info)
+
     def to(self, device) -> "TensorBatch":
         self.batch = {k: v.to(device, non_blocking=True) for k, v in self.batch.items()}
         return self

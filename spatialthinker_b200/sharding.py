@@ -89,6 +89,36 @@ class _Reversed:
         return self.key == other.key
 
 
+def micro_batch_counts(token_sums: Sequence[int], max_token_len: int, group: Optional["dist.ProcessGroup"] = None,
+                       device=None) -> List[int]:
+    """``ceil(tokens / max_token_len)`` per mini-batch, raised to the maximum over the data-parallel ranks so that every
+    rank runs the same number of micro-batches (seqlen_balancing.py:234-239). ONE collective for all mini-batches of a
+    call instead of one per mini-batch."""
+    nums = [max(1, -(-int(t) // int(max_token_len))) for t in token_sums]
+    if nums and dist.is_available() and dist.is_initialized() and _world(group) > 1:
+        backend = dist.get_backend(group)
+        t = torch.tensor(nums, dtype=torch.int64, device=device if backend == "nccl" else "cpu")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+        nums = [int(v) for v in t.tolist()]
+    return nums
+
+
+def rearrange_micro_batches(seq_lens: Sequence[int], max_token_len: int, group: Optional["dist.ProcessGroup"] = None,
+                            device=None, num_micro_batches: Optional[int] = None) -> List[List[int]]:
+    """Index lists of token-balanced micro-batches: seqlen_balancing.py:222-255 on the host-known token counts.
+
+    ``ceil(sum(seq_lens) / max_token_len)`` micro-batches (the maximum of that over the data-parallel ranks, :236-239 -
+    or ``num_micro_batches`` when the caller has already agreed on it, see :func:`micro_batch_counts`), items assigned
+    by :func:`balanced_partitions` with ``equal_size=False``, each list sorted by index. ``max_token_len`` must be at
+    least the longest sequence (:228-230)."""
+    lens = [int(x) for x in seq_lens]
+    assert lens and max_token_len >= max(lens), (
+        f"max_token_len must be greater than the sequence length. Got {max_token_len=} and max_seq_len={max(lens) if lens else 0}")
+    num = num_micro_batches if num_micro_batches is not None else micro_batch_counts([sum(lens)], max_token_len, group, device)[0]
+    assert num <= len(lens)
+    return balanced_partitions(lens, num, equal_size=False)
+
+
 def rank_rows(seqlens: Sequence[int], world_size: int, rank: int) -> List[int]:
     """Row ids this rank owns after token-balancing (equal sequence counts)."""
     return balanced_partitions(seqlens, world_size, equal_size=True)[rank]

@@ -17,7 +17,7 @@ def _worker(rank, world, port, out):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from oracle import grpo_oracle as O
-        from spatialthinker_b200.sharding import all_gather_rows, allreduce_mean_, rank_rows
+        from spatialthinker_b200.sharding import all_gather_rows, allreduce_mean_, rank_rows, rearrange_micro_batches
 
         bsz, t, v, hd, n = 16, 6, 128, 64, 4
         roll = O.synth_rollout(bsz, t, v, n, seed=3, ragged=True)  # identical on every rank
@@ -38,6 +38,11 @@ def _worker(rank, world, port, out):
         old = O.perturbed_log_probs(logp, seed=5)
         res = O.fused_loss_reference(hidden[mine], weight, roll["responses"][mine], old[mine], adv[mine],
                                      roll["response_mask"][mine], None)
+        # (2b) token-balanced micro-batches: every rank runs the MAXIMUM micro-batch count over the ranks
+        # (seqlen_balancing.py:236-239), here rank 1 alone would need fewer
+        my_lens = [40, 30, 20, 10, 25, 35] if rank == 0 else [5, 5, 5, 5, 5, 5]
+        parts = rearrange_micro_batches(my_lens, 60)
+        assert len(parts) == 3 and sorted(i for p in parts for i in p) == list(range(6))
         dw = res["dweight"].clone()
         allreduce_mean_(dw)  # (3) FSDP-style mean over ranks
         if rank == 0:

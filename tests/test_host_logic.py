@@ -31,7 +31,7 @@ def test_header_symbols_exported(lib):
     for name in declared:
         assert hasattr(raw, name), f"{name} declared in include/grpo_b200.h but not exported"
     assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
-    assert lib.grpo_abi_version() == 1
+    assert lib.grpo_abi_version() == 2
 
 
 def test_workspace_queries_are_host_only(lib):
@@ -192,7 +192,7 @@ def test_header_is_plain_c_and_links(lib, tmp_path):
     out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
     assert out.returncode == 0, out.stderr
     version, ws, rc, msg = out.stdout.split(maxsplit=3)
-    assert int(version) == 1 and int(ws) == lib.grpo_fused_loss_workspace_bytes(37888, 3584, 151936)
+    assert int(version) == 2 and int(ws) == lib.grpo_fused_loss_workspace_bytes(37888, 3584, 151936)
     assert int(rc) == -1 and "null" in msg
 
 
@@ -258,6 +258,7 @@ def test_deferred_dw_slot_bookkeeping():
 
     s = object.__new__(DeferredDW)  # no device: only the bookkeeping is exercised
     s.capacity, s.next_row0, s.total_rows, s.pending = 18944, 0, 0, 0
+    s.workspace = object()  # stands in for the lazily allocated device buffer
     flushed = []
 
     def flush():
@@ -271,3 +272,46 @@ def test_deferred_dw_slot_bookkeeping():
     assert s.reserve(1) == 0 and flushed == [(18944, 5)]  # did not fit: flushed, first slot again
     assert s.reserve(18945) is None and s.reserve(0) is None  # never fits / empty: ordinary path
     assert (s.total_rows, s.next_row0, s.pending) == (1, 512, 1)
+
+
+def test_rearrange_micro_batches_matches_reference():
+    """sharding.rearrange_micro_batches = verl/utils/seqlen_balancing.py:222-255 on host-known lengths: the same number of
+    micro-batches, and - when the reference checkout is present - the very same partitions."""
+    import random
+
+    from spatialthinker_b200.protocol import TensorBatch
+    from spatialthinker_b200.sharding import rearrange_micro_batches
+
+    rng = random.Random(4)
+    cases = [([rng.randint(1, 4096) for _ in range(n)], cap) for n, cap in ((16, 8192), (128, 37888), (7, 4096), (64, 5000))]
+    cases.append(([1024] * 128, 37888))
+    ref = None
+    ref_root = os.environ.get("GRPO_REFERENCE", "/root/reference")
+    if os.path.isdir(os.path.join(ref_root, "verl")):
+        sys.dont_write_bytecode = True
+        if ref_root not in sys.path:
+            sys.path.insert(0, ref_root)
+        try:
+            from verl.utils.seqlen_balancing import get_seqlen_balanced_partitions as ref
+        except Exception:  # tensordict is not installed here: load the two pure functions from the source file
+            import types
+
+            src = open(os.path.join(ref_root, "verl", "utils", "seqlen_balancing.py")).read()
+            src = src.replace("from tensordict import TensorDict", "TensorDict = object")
+            mod = types.ModuleType("_ref_seqlen_balancing")
+            exec(compile(src, "seqlen_balancing.py", "exec"), mod.__dict__)
+            ref = mod.get_seqlen_balanced_partitions
+    for lens, cap in cases:
+        parts = rearrange_micro_batches(lens, cap)
+        num = -(-sum(lens) // cap)
+        assert len(parts) == num and sorted(i for p in parts for i in p) == list(range(len(lens)))
+        assert all(p == sorted(p) for p in parts)
+        if ref is not None:
+            assert parts == ref(lens, num, equal_size=False)
+    with pytest.raises(AssertionError):
+        rearrange_micro_batches([100, 5000], 4096)  # a sequence longer than max_token_len (seqlen_balancing.py:228)
+    # TensorBatch.take builds the micro-batch the reference concatenates row by row (:245-251)
+    tb = TensorBatch({"x": torch.arange(12).view(6, 2)}, {"uid": np.array(list("abcdef"), dtype=object)}, {"t": 1.0})
+    mb = tb.take([4, 0, 5])
+    assert mb.batch["x"].tolist() == [[8, 9], [0, 1], [10, 11]] and mb.non_tensor_batch["uid"].tolist() == ["e", "a", "f"]
+    assert len(mb) == 3 and mb.meta_info == {"t": 1.0}
