@@ -11,7 +11,8 @@ stream through the reference's flash-attn varlen patch, which stays the referenc
 """
 from __future__ import annotations
 
-from typing import Any, Callable, Dict
+import dataclasses
+from typing import Any, Callable, Dict, Optional
 
 import torch
 
@@ -110,16 +111,21 @@ def make_hidden_fn(model: torch.nn.Module) -> Callable[[Dict[str, Any]], torch.T
 # ----------------------------------------------------------------------------------------------------------------
 # forward patch: the model returns .log_probs instead of .logits
 # ----------------------------------------------------------------------------------------------------------------
+@dataclasses.dataclass
 class FusedHeadOutput:
     """What a patched ``forward`` returns when it is given ``responses``: per-token log-probs of the response tokens
-    (and optionally their entropy, or the fused GRPO loss) instead of ``[bsz, seqlen, vocab]`` logits."""
+    (and optionally their entropy, or the fused GRPO loss) instead of ``[bsz, seqlen, vocab]`` logits.
 
-    __slots__ = ("log_probs", "entropy", "loss", "metrics", "logits", "last_hidden_state")
+    A dataclass on purpose: FSDP and DDP walk a module's outputs (``torch.distributed.utils._apply_to_tensors``: tensors,
+    dicts, tuples, dataclasses) to hang their pre-backward hooks on every tensor; an opaque object would leave the root
+    unit resharded when the head's backward runs."""
 
-    def __init__(self, log_probs, entropy=None, loss=None, metrics=None, last_hidden_state=None):
-        self.log_probs, self.entropy, self.loss, self.metrics = log_probs, entropy, loss, metrics
-        self.logits = None  # never materialised
-        self.last_hidden_state = last_hidden_state
+    log_probs: torch.Tensor
+    entropy: Optional[torch.Tensor] = None
+    loss: Optional[torch.Tensor] = None
+    metrics: Optional[Dict[str, Any]] = None
+    last_hidden_state: Optional[torch.Tensor] = None
+    logits: None = None  # never materialised
 
 
 _PATCH_ATTR = "_grpo_b200_original_forward"
@@ -176,12 +182,13 @@ def patch_model(model: torch.nn.Module) -> torch.nn.Module:
             weight = weight.to(torch.bfloat16)  # differentiable cast (fp32 master weights)
         if grpo is None:
             logp, ent = fused_lm_head_log_probs(rows, weight, responses, temperature, want_entropy)
-            return FusedHeadOutput(logp, ent, last_hidden_state=hidden)
+            return FusedHeadOutput(log_probs=logp, entropy=ent, last_hidden_state=hidden)
         g = dict(grpo)
         loss, metrics = fused_grpo_loss(rows, weight, responses, g.pop("old_log_probs"), g.pop("advantages"),
                                         g.pop("ref_log_probs", None), g.pop("response_mask"), temperature=temperature,
                                         want_entropy=want_entropy, **g)
-        return FusedHeadOutput(metrics.pop("log_probs"), metrics.pop("entropy", None), loss, metrics, hidden)
+        return FusedHeadOutput(log_probs=metrics.pop("log_probs"), entropy=metrics.pop("entropy", None), loss=loss,
+                               metrics=metrics, last_hidden_state=hidden)
 
     setattr(model, _PATCH_ATTR, original)
     model.forward = forward

@@ -29,23 +29,25 @@ def balanced_partitions(seqlens: Sequence[int], k: int, equal_size: bool = True)
     """
     n = len(seqlens)
     assert n >= k, f"number of items:[{n}] < k_partitions:[{k}]"
-    # A partial solution is a list of k bins, kept sorted by descending (sum, count, items); two solutions are merged
-    # by pairing the heaviest bin of one with the lightest of the other. The heap pops the solution with the largest
-    # spread (heaviest - lightest) first.
-    def bin_key(b):
-        return (b[0], len(b[1]), b[1])
+    # A partial solution ("state") is a list of k bins kept in DESCENDING order; a bin is the tuple
+    # (sum, count, items) with items a tuple of (index, length) pairs - exactly the fields the reference's Set.__lt__
+    # compares, in its order (seqlen_balancing.py:39-44), so plain tuple comparison reproduces its ordering without a key
+    # function. Two states are merged by pairing the heaviest bin of one with the lightest of the other. The heap pops
+    # the state with the largest spread (heaviest - lightest) first, ties going to the state whose heaviest bin is
+    # larger (State.__lt__, :77-83).
+    empty = (0, 0, ())
 
     def make_state(items):
-        bins = [(0, [])] * k
-        bins = [(length, [(idx, length)]) for idx, length in items] + [(0, []) for _ in range(k - len(items))]
-        bins.sort(key=bin_key, reverse=True)
+        bins = [(length, 1, ((idx, length),)) for idx, length in items] + [empty] * (k - len(items))
+        bins.sort(reverse=True)
         return bins
 
     def heap_entry(bins, serial):
-        spread = bins[0][0] - bins[-1][0]
-        top = bin_key(bins[0])
-        # max-spread first, then the state whose heaviest bin is larger; `serial` keeps comparisons total
-        return (-spread, _Reversed(top), serial, bins)
+        # min-heap keys, all plain ints: -spread, then "the larger heaviest bin first" = descending (sum, count, items).
+        # Item tuples of two different bins never share their first (index, length) pair (indices are distinct), so the
+        # first index decides wherever sum and count tie. `serial` keeps comparisons total.
+        top = bins[0]
+        return (bins[-1][0] - top[0], -top[0], -top[1], -(top[2][0][0] if top[1] else -1), serial, bins)
 
     by_len = sorted((int(length), idx) for idx, length in enumerate(seqlens))
     heap = []
@@ -54,39 +56,30 @@ def balanced_partitions(seqlens: Sequence[int], k: int, equal_size: bool = True)
         assert n % k == 0, f"{n} % {k} != 0"
         for off in range(0, n, k):
             items = [(idx, length) for length, idx in by_len[off:off + k]]
-            heapq.heappush(heap, heap_entry(make_state(items), serial))
+            heap.append(heap_entry(make_state(items), serial))
             serial += 1
     else:
         for length, idx in by_len:
-            heapq.heappush(heap, heap_entry(make_state([(idx, length)]), serial))
+            heap.append(heap_entry(make_state([(idx, length)]), serial))
             serial += 1
+    heapq.heapify(heap)
+    last = k - 1
     while len(heap) > 1:
-        a = heapq.heappop(heap)[3]
-        b = heapq.heappop(heap)[3]
-        merged = [(a[i][0] + b[k - 1 - i][0], a[i][1] + b[k - 1 - i][1]) for i in range(k)]
-        merged.sort(key=bin_key, reverse=True)
+        a = heapq.heappop(heap)[5]
+        b = heapq.heappop(heap)[5]
+        merged = []
+        for i in range(k):
+            x, y = a[i], b[last - i]
+            merged.append((x[0] + y[0], x[1] + y[1], x[2] + y[2]) if y[1] else x)
+        merged.sort(reverse=True)
         heapq.heappush(heap, heap_entry(merged, serial))
         serial += 1
-    parts = [sorted(idx for idx, _ in items) for _, items in heap[0][3]]
+    parts = [sorted(idx for idx, _ in items) for _, _, items in heap[0][5]]
     seen = sorted(i for p in parts for i in p)
     assert seen == list(range(n)) and all(len(p) > 0 for p in parts)
     if equal_size:
         assert all(len(p) * k == n for p in parts)
     return parts
-
-
-class _Reversed:
-    """Wrap a key so that larger compares as smaller (heapq is a min-heap)."""
-    __slots__ = ("key",)
-
-    def __init__(self, key):
-        self.key = key
-
-    def __lt__(self, other):
-        return self.key > other.key
-
-    def __eq__(self, other):
-        return self.key == other.key
 
 
 def micro_batch_counts(token_sums: Sequence[int], max_token_len: int, group: Optional["dist.ProcessGroup"] = None,

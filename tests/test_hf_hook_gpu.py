@@ -44,6 +44,27 @@ def tiny_qwen2_5_vl(vocab=1024, hidden=128):
     return transformers.Qwen2_5_VLForConditionalGeneration(cfg)
 
 
+def round_params_to_bf16_(model):
+    """The path's precision model (BASELINE.json north_star; actor/config.py:57 ``mp_param_dtype = bf16``): the final hidden
+    states and the lm_head weight are bf16 VALUES, everything after them is fp32. fp32 leaves holding bf16-representable
+    values keep autograd in fp32 for the comparison."""
+    with torch.no_grad():
+        for p in model.parameters():
+            p.copy_(p.to(torch.bfloat16).float())
+    return model
+
+
+def reference_response_logits(model, t_len, temperature, **inputs):
+    """``logits[:, -T-1:-1] / temperature`` as the reference computes them (dp_actor.py:141-151), with the final hidden
+    states rounded to bf16 (what a bf16 body emits; the cast is differentiable, straight-through) and the lm_head product
+    in fp32."""
+    from spatialthinker_b200 import hf_hook
+
+    hidden = hf_hook.transformer_body(model)(**inputs, use_cache=False).last_hidden_state
+    rows = hidden[:, -t_len - 1: -1].to(torch.bfloat16).float()
+    return torch.nn.functional.linear(rows, hf_hook.lm_head_weight(model).float()) / temperature
+
+
 def text_batch(bsz, prompt, t_len, vocab, dev, seed=0):
     g = torch.Generator().manual_seed(seed)
     ids = torch.randint(0, vocab - 30, (bsz, prompt + t_len), generator=g)
@@ -59,7 +80,7 @@ def test_qwen2_5_vl_patched_forward_matches_logits_path(dev):
     from spatialthinker_b200 import hf_hook
 
     bsz, prompt, t_len, vocab = 2, 14, 8, 1024
-    model = tiny_qwen2_5_vl(vocab).to(dev).train()  # fp32 master weights; the head casts its operands to bf16
+    model = round_params_to_bf16_(tiny_qwen2_5_vl(vocab).to(dev).train())  # fp32 leaves, bf16-representable values
     ids, mask, pos = text_batch(bsz, prompt, t_len, vocab, dev)
     ids[:, 4:8] = 1000  # one 4 x 4-patch image per sequence = 4 merged image tokens
     pos3 = pos.unsqueeze(0).expand(3, bsz, -1).contiguous()
@@ -72,7 +93,9 @@ def test_qwen2_5_vl_patched_forward_matches_logits_path(dev):
 
     # reference: the unpatched model's logits, sliced and divided exactly like dp_actor.py:148-151, fp32 cross-entropy
     logits = model(input_ids=ids, attention_mask=mask, position_ids=pos3, use_cache=False, **extra).logits
-    z = logits[:, -t_len - 1: -1].float() / temperature
+    z = reference_response_logits(model, t_len, temperature, input_ids=ids, attention_mask=mask, position_ids=pos3, **extra)
+    # ... which is the model's own .logits path up to the bf16 rounding of the hidden rows
+    assert float((z - logits[:, -t_len - 1: -1] / temperature).abs().max()) < 3e-2
     want_lp = O.log_probs_from_logits(z, responses)
     want_ent = O.entropy_from_logits(z)
     ((want_lp * coef).sum() + 0.1 * want_ent.sum()).backward()
@@ -110,14 +133,14 @@ def test_patched_forward_fused_grpo_loss_and_padding_free(dev):
     from spatialthinker_b200 import hf_hook
 
     bsz, prompt, t_len, vocab = 4, 10, 12, 1024
-    model = tiny_qwen2(vocab=vocab).to(dev).train()
+    model = round_params_to_bf16_(tiny_qwen2(vocab=vocab).to(dev).train())
     ids, mask, pos = text_batch(bsz, prompt, t_len, vocab, dev, seed=3)
     responses = ids[:, -t_len:]
     g = torch.Generator().manual_seed(4)
     rmask = (torch.arange(t_len)[None] < torch.randint(3, t_len + 1, (bsz, 1), generator=g)).long().to(dev)
     adv = torch.randn(bsz, 1, generator=g).expand(bsz, t_len).contiguous().to(dev)
-    logits = model(input_ids=ids, attention_mask=mask, position_ids=pos, use_cache=False).logits
-    lp_ref = O.log_probs_from_logits(logits[:, -t_len - 1: -1].float(), responses)
+    z = reference_response_logits(model, t_len, 1.0, input_ids=ids, attention_mask=mask, position_ids=pos)
+    lp_ref = O.log_probs_from_logits(z, responses)
     old = O.perturbed_log_probs(lp_ref.detach().cpu(), seed=5, outlier_frac=0.05).to(dev)
     ref_lp = O.perturbed_log_probs(lp_ref.detach().cpu(), seed=6, outlier_frac=0.05).to(dev)
     loss_ref, met_ref = O.micro_batch_loss(lp_ref, old, adv, rmask, ref_lp, kl_penalty="low_var_kl", kl_coef=0.01,
@@ -188,11 +211,13 @@ def test_patched_forward_under_fsdp_root_unit(dev):
                 logits = fsdp(input_ids=ids, attention_mask=mask, position_ids=pos, use_cache=False).logits
                 lp = O.log_probs_from_logits(logits[:, -t_len - 1: -1].float() / 0.9, responses)
             (lp * coef).sum().backward()
-            with FSDP.summon_full_params(fsdp, with_grads=True):
-                grads[patched] = {n: p.grad.detach().float().clone() for n, p in model.named_parameters() if p.grad is not None}
+            # use_orig_params=False: the gradients live on the flat parameters (one for the root unit - embed_tokens /
+            # lm_head (tied) + final norm - and one per decoder layer); both models are built identically, so the flat
+            # layouts agree name by name
+            grads[patched] = {n: p.grad.detach().float().clone() for n, p in fsdp.named_parameters() if p.grad is not None}
             grads[("lp", patched)] = lp.detach()
         assert float((grads[("lp", True)] - grads[("lp", False)]).abs().max()) < 2e-2  # the unpatched path rounds logits to bf16
-        assert set(grads[True]) == set(grads[False]) and "model.embed_tokens.weight" in grads[True]
+        assert set(grads[True]) == set(grads[False]) and len(grads[True]) == 3
         for n in grads[True]:
             assert rel(grads[True][n], grads[False][n]) < 3e-2, n  # both bodies run in bf16; the unpatched head too
     finally:
