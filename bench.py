@@ -115,7 +115,7 @@ def global_layout(cfg, world, ragged, balance):
     """Response lengths and uids of the whole rollout batch, reordered so that rank r owns rows [r*local, (r+1)*local):
     token-balanced with equal sequence counts exactly like the reference's driver does before dispatch
     (_balance_batch, verl/trainer/ray_trainer.py:526-541 -> seqlen_balancing.py:150-181) when the batch is ragged."""
-    from spatialthinker_b200.sharding import balanced_partitions
+    from spatialthinker_b200.sharding import balanced_rank_order
 
     _, _, bsz, tlen, n, _ = cfg
     gp = torch.Generator().manual_seed(7)
@@ -127,18 +127,22 @@ def global_layout(cfg, world, ragged, balance):
     local = bsz // world
     naive = [int(lens[r * local:(r + 1) * local].sum()) for r in range(world)]
     if ragged and balance and world > 1:
-        parts = balanced_partitions(lens.tolist(), world, equal_size=True)
-        order = torch.tensor([i for p in parts for i in p])
+        # balance == 1: the reference's one partition of the whole batch; balance == 2 (default): every optimizer step's
+        # mini-batch balanced across the ranks as well (sharding.balanced_rank_order)
+        order = torch.tensor(balanced_rank_order(lens.tolist(), world, OPT_STEPS if balance > 1 else 1))
         lens, uid = lens[order], uid[order]
     per_rank = [int(lens[r * local:(r + 1) * local].sum()) for r in range(world)]
-    return lens, uid.numpy(), per_rank, naive
+    mini = max(local // OPT_STEPS, 1)
+    cells = [[int(lens[r * local + m * mini:r * local + (m + 1) * mini].sum()) for r in range(world)] for m in range(local // mini)]
+    spread = max((max(c) - min(c)) / max(max(c), 1) for c in cells)  # worst relative token imbalance at an optimizer step
+    return lens, uid.numpy(), per_rank, naive, spread
 
 
 def make_inputs(st, cfg, rank, world, dev, ragged, legacy, balance):
     hdim, vocab, bsz, tlen, n, _ = cfg
     assert bsz % world == 0
     local = bsz // world
-    lens_all, uid_all, per_rank, naive = global_layout(cfg, world, ragged, balance)
+    lens_all, uid_all, per_rank, naive, spread = global_layout(cfg, world, ragged, balance)
     lens = lens_all[rank * local:(rank + 1) * local].to(dev)
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     gw = torch.Generator(device=dev).manual_seed(99)  # the weight is replicated: same seed on every rank
@@ -176,7 +180,8 @@ def make_inputs(st, cfg, rank, world, dev, ragged, legacy, balance):
         old, ref = perturbed(), perturbed()
         del logp
     return {"weight": weight, "hidden": hidden, "labels": labels, "mask": mask, "rewards": rewards, "uid_np": uid_all,
-            "old": old, "ref": ref, "local": local, "lens": lens, "tokens_per_rank": per_rank, "tokens_per_rank_unbalanced": naive}
+            "old": old, "ref": ref, "local": local, "lens": lens, "tokens_per_rank": per_rank, "tokens_per_rank_unbalanced": naive,
+            "mini_batch_token_spread": spread}
 
 
 def actor_config(st, local, micro_seqs, want_entropy, entropy_coeff):
@@ -389,7 +394,9 @@ def main():
     ap.add_argument("--no-defer-dw", action="store_true", help="actor without the deferred dW GEMM for small micro-batches")
     ap.add_argument("--direct", action="store_true", help="round-1 loop over grpo_micro_batch_step instead of the actor (A/B)")
     ap.add_argument("--legacy-inputs", action="store_true", help="round-1 old/ref log-probs (-3 + 0.1 randn)")
-    ap.add_argument("--no-balance", action="store_true", help="ragged config: contiguous rank shards instead of token-balanced ones")
+    ap.add_argument("--balance", type=int, default=2, choices=[0, 1, 2],
+                    help="ragged config: 0 = contiguous rank shards, 1 = the reference's token-balanced shards (_balance_batch), "
+                         "2 = every optimizer step's mini-batch balanced across the ranks as well")
     ap.add_argument("--no-records", action="store_true", help="skip the extra record at 4-sequence micro-batches")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -427,7 +434,7 @@ def main():
     hdim, vocab, bsz, tlen, n, desc = cfg
     ragged = args.config == "c5"
     want_entropy = args.config == "c4"
-    x = make_inputs(st, cfg, rank, world, dev, ragged, args.legacy_inputs, not args.no_balance)
+    x = make_inputs(st, cfg, rank, world, dev, ragged, args.legacy_inputs, args.balance)
     tokens_local = int(x["mask"].sum().item())
     tok = torch.tensor([tokens_local], dtype=torch.float64, device=dev)
     if world > 1:
@@ -464,6 +471,8 @@ def main():
         dev_step = lambda: seen.update(m=run_step_device(st, actor, x, world))  # noqa: E731
     for _ in range(args.warmup):
         dev_step()
+    actor.time_collectives = world > 1
+    actor.collective_events = []
     sampler = ClockSampler(local_rank)
     launches0 = lib.grpo_launch_count()
     lib.grpo_profile_enable(1)
@@ -479,6 +488,17 @@ def main():
     lib.grpo_profile_enable(0)
     ms_per_step = ms_total / args.steps
     value = tokens_total / (ms_per_step * 1e-3)
+    # per rank: time inside the dW all-reduces per step (wire + waiting for the slowest rank) and in this rank's own GEMMs
+    actor.time_collectives = False
+    ar_ms = sum(a.elapsed_time(b) for a, b in actor.collective_events) / args.steps
+    per_rank = torch.tensor([ar_ms, sum(ph_ms[i] for i in range(_lib.NUM_PHASES)) / args.steps], dtype=torch.float64, device=dev)
+    gathered = [torch.zeros_like(per_rank) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(gathered, per_rank)
+    else:
+        gathered = [per_rank]
+    by_rank = {"allreduce_ms_per_step": [round(float(g[0]), 2) for g in gathered],
+               "kernel_phase_ms_per_step": [round(float(g[1]), 1) for g in gathered]}
     n_micro = None if args.direct else len(seen["m"]["actor/pg_loss"])
 
     # ---- the reference's shipped micro-batch size (4 sequences) with the deferred dW GEMM, a few steps
@@ -552,9 +572,10 @@ def main():
                    "inputs": "round-1 (-3 + 0.1 randn)" if args.legacy_inputs else "SURVEY 8(d): old/ref = logp + 0.1 randn, 1% +-1.5 outliers",
                    "loss": "GRPO clip .2/.3/3.0 + low_var_kl 1e-2" + (f" - {args.entropy_coeff} * entropy" if args.entropy_coeff else ""),
                    "l2": "inputs (>= 30 GB) far exceed the 126 MB L2",
-                   "parallelism": f"dp{world} by sequence" + (", token-balanced rank shards (Karmarkar-Karp)" if ragged and not args.no_balance else "") + ", dW mean all-reduce (NCCL)",
+                   "parallelism": f"dp{world} by sequence" + ((", token-balanced rank shards (Karmarkar-Karp" + (", per optimizer step" if args.balance > 1 else "") + ")") if ragged and args.balance else "") + ", dW mean all-reduce (NCCL)",
                    "tokens_per_rank": x["tokens_per_rank"], "tokens_per_rank_unbalanced": x["tokens_per_rank_unbalanced"],
-                   "records": records},
+                   "mini_batch_token_spread_across_ranks": x["mini_batch_token_spread"],
+                   "records": records, "by_rank": by_rank},
         "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline, "e2e": e2e,
     }
     if not args.no_cpu:

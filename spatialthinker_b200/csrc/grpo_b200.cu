@@ -555,6 +555,7 @@ static int chunk_forward(const DevInfo& dev, const Workspace& w, const __nv_bflo
     s.hint_a = kEvictLast;
     s.hint_b = kEvictFirst;
   }
+  if (dev.l2_hints & 8) s.hint_a = kEvictLast;  // only the hidden panel pinned; W at normal priority
   GRPO_CUDA(cudaMemsetAsync(w.sync, 0, 64, stream));
   {
     PhaseScope ps(PH_LOGITS_GEMM, stream);
@@ -600,6 +601,8 @@ static int dw_gemm(const DevInfo& dev, const Workspace& w, const __nv_bfloat16* 
     s.hint_a = kEvictFirst;
     s.hint_b = kEvictLast;
   }
+  if (dev.l2_hints & 4) s.hint_b = kEvictLast;  // only the scaled hidden pinned; the stash panel (shared by the 14 column
+                                                // tiles of a vocab block running side by side) at normal priority
   GRPO_TRY((launch_gemm_any<A_BLOCKED_MN, true, EpiF32<1, kBlockN>, EpiF32<2, kBlockN>>(
       dev, w.stash, v, w.stash_vb, b_op, h, h, n, s, p1, p2, stream)));
   return 0;
@@ -685,6 +688,7 @@ static int chunk_backward(const DevInfo& dev, const Workspace& w, const __nv_bfl
     s.sync_period = static_cast<uint32_t>(dev.sync_dh);
     s.sync_ctr = w.sync + 1;
     s.probe = dev.clk_probe ? w.probe + 1024 : nullptr;
+    if (dev.l2_hints & 16) s.hint_b = kEvictLast;  // W is re-read by every round of tiles; the stash streams through once
     GRPO_TRY((launch_gemm_any<A_BLOCKED_K, true, EpiBF16<1, kBlockN>, EpiBF16<2, kBlockN>>(
         dev, w.stash, n, w.stash_vb, weight, h, h, v, s, p1, p2, stream)));
   }

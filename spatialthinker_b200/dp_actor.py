@@ -227,6 +227,10 @@ class DataParallelPPOActor:
         self._grad_buf: Optional[torch.Tensor] = None  # bf16 [V, H]: what the optimizer sees as weight.grad
         self._stager: Optional[_HostStager] = None     # staging buffers of host-resident batches (kept across calls)
         self._warned_body = False
+        # measurement aid (bench.py): CUDA events around every dW all-reduce; the time the slowest-arriving rank spends in
+        # it is the wire time, what the others spend on top of that is waiting for it
+        self.time_collectives = False
+        self.collective_events: List[tuple] = []
         self.last_dhidden: List[torch.Tensor] = []   # per micro-batch dHidden of the last update (when no hidden_fn)
         if config.deterministic:
             _lib.check(_lib.load().grpo_set_option(b"deterministic", 1), "grpo_set_option")
@@ -276,7 +280,14 @@ class DataParallelPPOActor:
         a non-finite norm skips the update (the reference's host branch) and the gradients are dropped."""
         assert self.dweight is not None
         cfg = self.config
-        allreduce_mean_(self.dweight, self.process_group)
+        if self.time_collectives:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            allreduce_mean_(self.dweight, self.process_group)
+            e1.record()
+            self.collective_events.append((e0, e1))
+        else:
+            allreduce_mean_(self.dweight, self.process_group)
         opt = self.actor_optimizer
         if opt is None:  # head-only accumulation (bench, tests): norm and zeroing share one pass over dW
             return grad_sumsq(self.dweight, zero_after=True).sqrt().float().squeeze(0)

@@ -117,6 +117,29 @@ def rank_rows(seqlens: Sequence[int], world_size: int, rank: int) -> List[int]:
     return balanced_partitions(seqlens, world_size, equal_size=True)[rank]
 
 
+def balanced_rank_order(seqlens: Sequence[int], world_size: int, mini_batches: int = 1) -> List[int]:
+    """Row order for dispatching a rollout batch to ``world_size`` data-parallel ranks: rank ``r`` owns rows
+    ``order[r * local : (r + 1) * local]`` (``local = len(seqlens) / world_size``).
+
+    ``mini_batches == 1`` is the reference's ``_balance_batch`` (ray_trainer.py:526-541): one Karmarkar-Karp partition of
+    the whole batch, equal sequence counts, balanced token sums per rank. The ranks meet at EVERY optimizer step (the
+    gradient all-reduce), though, and the reference then cuts each rank's shard into consecutive mini-batches
+    (dp_actor.py:227) whose token sums are whatever they happen to be - at 256 ragged sequences per mini-batch they differ
+    by +-3.6 % between ranks and the fast ranks wait at each all-reduce. ``mini_batches = M > 1`` balances both ways: the
+    batch is first split into ``M`` groups of equal size and token sum, then each group over the ranks; rank ``r``'s
+    ``m``-th consecutive mini-batch is its part of group ``m``, so every (rank, mini-batch) cell carries the same number of
+    sequences and (nearly) the same number of tokens."""
+    n = len(seqlens)
+    assert n % (world_size * mini_batches) == 0, f"{n} % ({world_size} * {mini_batches}) != 0"
+    lens = [int(x) for x in seqlens]
+    groups = balanced_partitions(lens, mini_batches, equal_size=True) if mini_batches > 1 else [list(range(n))]
+    cells = []  # cells[m][r] = global row ids
+    for group in groups:
+        parts = balanced_partitions([lens[i] for i in group], world_size, equal_size=True)
+        cells.append([[group[j] for j in part] for part in parts])
+    return [i for r in range(world_size) for m in range(len(groups)) for i in cells[m][r]]
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # collectives
 # ----------------------------------------------------------------------------------------------------------------

@@ -117,13 +117,13 @@ def check_step(res, want, mask, *, use_ref, want_entropy):
         assert float(dh[~valid].abs().max()) == 0.0  # masked rows: exactly zero gradient
 
 
-def make_case(bsz, tl, vocab, n, *, seed, sigma, ragged, dev):
+def make_case(bsz, tl, vocab, n, *, seed, sigma, ragged, dev, hdim=H7B):
     """Seeded synthetic micro-batch at the 7B head (SURVEY §8d generator): labels half sampled uniformly, half the row
     arg-max (so that both improbable and probable labels occur), old / ref = oracle log-probs + jitter + outliers."""
-    hid, w = O.synth_head(bsz * tl, H7B, vocab, seed=seed, sigma_w=sigma)
+    hid, w = O.synth_head(bsz * tl, hdim, vocab, seed=seed, sigma_w=sigma)
     roll = O.synth_rollout(bsz, tl, vocab, n, seed=seed, ragged=ragged)
     adv, _ = O.compute_grpo_outcome_advantage(roll["token_level_rewards"].clone(), roll["response_mask"], roll["uid"])
-    return {"hidden": hid.view(bsz, tl, H7B).to(dev), "weight": w.to(dev), "labels": roll["responses"].to(dev),
+    return {"hidden": hid.view(bsz, tl, hdim).to(dev), "weight": w.to(dev), "labels": roll["responses"].to(dev),
             "mask": roll["response_mask"].to(dev), "adv": adv.to(dev), "lens": roll["response_mask"].sum(-1)}
 
 
@@ -150,6 +150,23 @@ def test_7b_head_2048_rows_vs_cpu_oracle(st, dev, vocab, sigma, temp):
     lp, ent = st.fused_lm_head_log_probs(x["hidden"], x["weight"], x["labels"], temp, want_entropy=True)
     assert float((lp.cpu() - want["log_probs"]).abs().max()) < TOL_LOGP
     assert float((ent.cpu() - want["entropy"]).abs().max()) < TOL_LOGP
+
+
+def test_3b_head_config_c2_shape_vs_cpu_oracle(st, dev):
+    """BASELINE configs[1]: the Qwen2.5-VL-3B head (H = 2048, V = 151 936) - 2048 rows of it against the CPU oracle. With
+    K = 2048 the logits GEMM's tiles are 32 K-blocks long and the dHidden GEMM has 8 column blocks per row tile."""
+    bsz, tl, n, hdim = 8, 256, 8, 2048
+    x = make_case(bsz, tl, V_QWEN, n, seed=77, sigma=0.05, ragged=True, dev=dev, hdim=hdim)
+    hid_c, w_c, lab_c, mask_c, adv_c = (x[k].cpu() for k in ("hidden", "weight", "labels", "mask", "adv"))
+    logp_c, _ = O.lm_head_log_probs(hid_c, w_c, lab_c, 1.0)
+    old, ref = O.perturbed_log_probs(logp_c, seed=1, outlier_frac=0.02), O.perturbed_log_probs(logp_c, seed=2, outlier_frac=0.02)
+    want = O.fused_loss_reference(hid_c, w_c, lab_c, old, adv_c, mask_c, ref, temperature=1.0, kl_penalty="low_var_kl",
+                                  kl_coef=1e-2, grad_accum=2.0, want_entropy=True, **CLIP)
+    res = st.grpo_micro_batch_step(x["hidden"], x["weight"], x["labels"], old.to(dev), x["adv"], ref.to(dev), x["mask"],
+                                   temperature=1.0, kl_penalty="low_var_kl", kl_coef=1e-2, grad_accum=2.0,
+                                   want_entropy=True, **CLIP)
+    torch.cuda.synchronize()
+    check_step(res, want, x["mask"], use_ref=True, want_entropy=True)
 
 
 # ================================================================================================ (ii) across a real chunk boundary

@@ -11,5 +11,5 @@ $RUN --master-port 29512 bench.py --gpus $N --config c4 --steps 4 --warmup 2 > g
 cut -c1-600 gpurun_out/r2_bench_c4_${N}gpu.json; tail -2 gpurun_out/r2_bench_c4_${N}gpu.err
 $RUN --master-port 29513 bench.py --gpus $N --config c5 --steps 3 --warmup 2 --no-e2e > gpurun_out/r2_bench_c5_${N}gpu.json 2> gpurun_out/r2_bench_c5_${N}gpu.err
 cut -c1-600 gpurun_out/r2_bench_c5_${N}gpu.json; tail -2 gpurun_out/r2_bench_c5_${N}gpu.err
-$RUN --master-port 29514 bench.py --gpus $N --config c5 --steps 3 --warmup 2 --no-e2e --no-cpu --no-records --no-balance > gpurun_out/r2_bench_c5_${N}gpu_unbalanced.json 2> gpurun_out/r2_bench_c5_${N}gpu_unbalanced.err
+$RUN --master-port 29514 bench.py --gpus $N --config c5 --steps 3 --warmup 2 --no-e2e --no-cpu --no-records --balance 0 > gpurun_out/r2_bench_c5_${N}gpu_unbalanced.json 2> gpurun_out/r2_bench_c5_${N}gpu_unbalanced.err
 cut -c1-400 gpurun_out/r2_bench_c5_${N}gpu_unbalanced.json; tail -2 gpurun_out/r2_bench_c5_${N}gpu_unbalanced.err
