@@ -111,11 +111,14 @@ class ClockSampler:
 # synthetic workload: the GLOBAL batch structure (lengths, uids, rank assignment) is generated
 # identically on every rank, this rank's tensors on its device
 # ------------------------------------------------------------------------------------------------------------------
-def global_layout(cfg, world, ragged, balance):
-    """Response lengths and uids of the whole rollout batch, reordered so that rank r owns rows [r*local, (r+1)*local):
-    token-balanced with equal sequence counts exactly like the reference's driver does before dispatch
-    (_balance_batch, verl/trainer/ray_trainer.py:526-541 -> seqlen_balancing.py:150-181) when the batch is ragged."""
-    from spatialthinker_b200.sharding import balanced_rank_order
+def global_layout(cfg, world, ragged, balance, counts=None, step_times=None):
+    """Response lengths and uids of the whole rollout batch in dispatch order: rank r owns rows [offset_r, offset_r + count_r).
+
+    Equal counts (default): token-balanced exactly like the reference's driver does before dispatch (_balance_batch,
+    verl/trainer/ray_trainer.py:526-541 -> seqlen_balancing.py:150-181) when the batch is ragged, and additionally per
+    optimizer step (balance == 2). ``counts`` / ``step_times`` (speed-aware shards): rank r gets counts[r] sequences and,
+    for a ragged batch, tokens in proportion to its measured speed in every mini-batch."""
+    from spatialthinker_b200.sharding import balanced_rank_order, weighted_balanced_cells
 
     _, _, bsz, tlen, n, _ = cfg
     gp = torch.Generator().manual_seed(7)
@@ -125,25 +128,36 @@ def global_layout(cfg, world, ragged, balance):
     else:
         lens = torch.full((bsz,), tlen, dtype=torch.long)
     local = bsz // world
+    equal = counts is None or all(c == local for c in counts)
+    counts = [local] * world if counts is None else list(counts)
+    offsets = [sum(counts[:r]) for r in range(world)]
     naive = [int(lens[r * local:(r + 1) * local].sum()) for r in range(world)]
     if ragged and balance and world > 1:
-        # balance == 1: the reference's one partition of the whole batch; balance == 2 (default): every optimizer step's
-        # mini-batch balanced across the ranks as well (sharding.balanced_rank_order)
-        order = torch.tensor(balanced_rank_order(lens.tolist(), world, OPT_STEPS if balance > 1 else 1))
+        if equal:
+            # balance == 1: the reference's one partition of the whole batch; balance == 2 (default): every optimizer step's
+            # mini-batch balanced across the ranks as well (sharding.balanced_rank_order)
+            order = torch.tensor(balanced_rank_order(lens.tolist(), world, OPT_STEPS if balance > 1 else 1))
+        else:
+            sizes = [c // OPT_STEPS for c in counts for _ in range(OPT_STEPS)]
+            weights = [1.0 / step_times[r] for r in range(world) for _ in range(OPT_STEPS)]
+            cells = weighted_balanced_cells(lens.tolist(), sizes, weights)
+            order = torch.tensor([i for cell in cells for i in cell])
         lens, uid = lens[order], uid[order]
-    per_rank = [int(lens[r * local:(r + 1) * local].sum()) for r in range(world)]
-    mini = max(local // OPT_STEPS, 1)
-    cells = [[int(lens[r * local + m * mini:r * local + (m + 1) * mini].sum()) for r in range(world)] for m in range(local // mini)]
-    spread = max((max(c) - min(c)) / max(max(c), 1) for c in cells)  # worst relative token imbalance at an optimizer step
-    return lens, uid.numpy(), per_rank, naive, spread
+    per_rank = [int(lens[offsets[r]:offsets[r] + counts[r]].sum()) for r in range(world)]
+    # worst relative imbalance of PREDICTED time at an optimizer step (tokens x the rank's time per token)
+    tpt = [1.0] * world if step_times is None else [step_times[r] for r in range(world)]
+    cells = [[float(lens[offsets[r] + m * (counts[r] // OPT_STEPS):offsets[r] + (m + 1) * (counts[r] // OPT_STEPS)].sum()) * tpt[r]
+              for r in range(world)] for m in range(OPT_STEPS)] if all(c >= OPT_STEPS for c in counts) else [[1.0]]
+    spread = max((max(c) - min(c)) / max(max(c), 1e-9) for c in cells)
+    return lens, uid.numpy(), per_rank, naive, spread, counts, offsets
 
 
-def make_inputs(st, cfg, rank, world, dev, ragged, legacy, balance):
+def make_inputs(st, cfg, rank, world, dev, ragged, legacy, balance, counts=None, step_times=None):
     hdim, vocab, bsz, tlen, n, _ = cfg
     assert bsz % world == 0
-    local = bsz // world
-    lens_all, uid_all, per_rank, naive, spread = global_layout(cfg, world, ragged, balance)
-    lens = lens_all[rank * local:(rank + 1) * local].to(dev)
+    lens_all, uid_all, per_rank, naive, spread, counts, offsets = global_layout(cfg, world, ragged, balance, counts, step_times)
+    local = counts[rank]
+    lens = lens_all[offsets[rank]:offsets[rank] + local].to(dev)
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     gw = torch.Generator(device=dev).manual_seed(99)  # the weight is replicated: same seed on every rank
     weight = torch.empty(vocab, hdim, dtype=torch.bfloat16, device=dev)
@@ -179,15 +193,19 @@ def make_inputs(st, cfg, rank, world, dev, ragged, legacy, balance):
 
         old, ref = perturbed(), perturbed()
         del logp
+    equal = all(c == counts[0] for c in counts)
     return {"weight": weight, "hidden": hidden, "labels": labels, "mask": mask, "rewards": rewards, "uid_np": uid_all,
             "old": old, "ref": ref, "local": local, "lens": lens, "tokens_per_rank": per_rank, "tokens_per_rank_unbalanced": naive,
-            "mini_batch_token_spread": spread}
+            "mini_batch_token_spread": spread, "row_begin": offsets[rank], "rank_sizes": None if equal else counts,
+            "counts": counts, "nominal_local": bsz // world}
 
 
-def actor_config(st, local, micro_seqs, want_entropy, entropy_coeff):
-    mini = max(local // OPT_STEPS, 1)
-    kw = dict(global_batch_size_per_device=mini, use_kl_loss=True, kl_penalty=KL["kl_penalty"], kl_coef=KL["kl_coef"],
-              log_true_entropy=want_entropy, entropy_coeff=entropy_coeff, **CLIP)
+def actor_config(st, x, micro_seqs, want_entropy, entropy_coeff):
+    mini = max(x["local"] // OPT_STEPS, 1)
+    # speed-aware shards: every rank scales its losses for the NOMINAL mini-batch size, whatever it holds itself
+    nominal = 0 if x["rank_sizes"] is None else max(x["nominal_local"] // OPT_STEPS, 1)
+    kw = dict(global_batch_size_per_device=mini, loss_scale_batch_size=nominal, use_kl_loss=True, kl_penalty=KL["kl_penalty"],
+              kl_coef=KL["kl_coef"], log_true_entropy=want_entropy, entropy_coeff=entropy_coeff, **CLIP)
     if micro_seqs:
         return st.ActorConfig(micro_batch_size_per_device_for_update=micro_seqs, **kw)
     return st.ActorConfig(use_dynamic_bsz=True, max_token_len_per_micro_batch=MAX_TOKENS, **kw)
@@ -199,8 +217,8 @@ def actor_config(st, local, micro_seqs, want_entropy, entropy_coeff):
 def run_step_device(st, actor, x, world):
     # advantages: groups straddle ranks, so the per-sequence scores are all-gathered (B floats) and the group statistics
     # run redundantly per rank; this rank's rows are then broadcast over its response mask
-    rank = dist.get_rank() if world > 1 else 0
-    adv, _ = st.core_algos.compute_grpo_outcome_advantage_sharded(x["rewards"], x["mask"], x["uid_np"], rank * x["local"])
+    adv, _ = st.core_algos.compute_grpo_outcome_advantage_sharded(x["rewards"], x["mask"], x["uid_np"], x["row_begin"],
+                                                                  rank_sizes=x["rank_sizes"])
     data = st.TensorBatch({"hidden_states": x["hidden"], "responses": x["labels"], "response_mask": x["mask"],
                            "old_log_probs": x["old"], "ref_log_probs": x["ref"], "advantages": adv},
                           meta_info={"temperature": 1.0})
@@ -212,8 +230,8 @@ def run_step_direct(st, x, plan, dweight, world, want_entropy, entropy_coeff, co
     from spatialthinker_b200.dp_actor import grad_sumsq
     from spatialthinker_b200.sharding import allreduce_mean_
 
-    rank = dist.get_rank() if world > 1 else 0
-    adv, _ = st.core_algos.compute_grpo_outcome_advantage_sharded(x["rewards"], x["mask"], x["uid_np"], rank * x["local"])
+    adv, _ = st.core_algos.compute_grpo_outcome_advantage_sharded(x["rewards"], x["mask"], x["uid_np"], x["row_begin"],
+                                                                  rank_sizes=x["rank_sizes"])
     metrics, norms = [], []
     for mbs in plan:
         ga = float(len(mbs))
@@ -257,12 +275,12 @@ class HostBatch:
 
 
 def run_step_e2e(st, actor, x, host, world):
-    rank = dist.get_rank() if world > 1 else 0
     # rewards + mask host -> device, advantages on the device, back to the host batch (the reference computes them on the
     # driver and ships them with the batch: ray_trainer.py:148-175)
     host.rewards_dev.copy_(host.t["rewards"], non_blocking=True)
     host.mask_dev.copy_(host.t["mask"], non_blocking=True)
-    adv, _ = st.core_algos.compute_grpo_outcome_advantage_sharded(host.rewards_dev, host.mask_dev, x["uid_np"], rank * x["local"])
+    adv, _ = st.core_algos.compute_grpo_outcome_advantage_sharded(host.rewards_dev, host.mask_dev, x["uid_np"], x["row_begin"],
+                                                                  rank_sizes=x["rank_sizes"])
     host.adv.copy_(adv, non_blocking=True)
     torch.cuda.current_stream().synchronize()
     data = st.TensorBatch({"hidden_states": host.t["hidden"], "responses": host.t["labels"], "response_mask": host.t["mask"],
@@ -398,6 +416,8 @@ def main():
                     help="ragged config: 0 = contiguous rank shards, 1 = the reference's token-balanced shards (_balance_batch), "
                          "2 = every optimizer step's mini-batch balanced across the ranks as well")
     ap.add_argument("--no-records", action="store_true", help="skip the extra record at 4-sequence micro-batches")
+    ap.add_argument("--no-speed-aware", action="store_true",
+                    help="N > 1: keep equal sequence counts per rank (default: re-deal sequences by measured per-rank speed)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -435,11 +455,15 @@ def main():
     ragged = args.config == "c5"
     want_entropy = args.config == "c4"
     x = make_inputs(st, cfg, rank, world, dev, ragged, args.legacy_inputs, args.balance)
-    tokens_local = int(x["mask"].sum().item())
-    tok = torch.tensor([tokens_local], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tok)
-    tokens_total = float(tok.item())
+
+    def count_tokens(xx):
+        local = int(xx["mask"].sum().item())
+        tok = torch.tensor([local], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tok)
+        return local, float(tok.item())
+
+    tokens_local, tokens_total = count_tokens(x)
 
     def sync_all():
         if world > 1:
@@ -459,8 +483,43 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    actor = st.DataParallelPPOActor(actor_config(st, x["local"], args.micro_seqs, want_entropy, args.entropy_coeff),
-                                    x["weight"], defer_dw=not args.no_defer_dw)
+    def build_actor(xx, micro_seqs=args.micro_seqs, defer=not args.no_defer_dw):
+        return st.DataParallelPPOActor(actor_config(st, xx, micro_seqs, want_entropy, args.entropy_coeff), xx["weight"],
+                                       defer_dw=defer)
+
+    actor = build_actor(x)
+    # ---- speed-aware shards (N > 1): the chips of one box differ by several percent in sustained throughput under the
+    # power cap and meet at every optimizer step; the first warm-up steps on EQUAL shards measure every rank's own kernel
+    # time per step, then sequences are re-dealt in proportion to speed (sharding.speed_weighted_counts) and one more
+    # warm-up step runs on the new shards. All of it before the timed region.
+    speed_aware = None
+    warm_done = 0
+    if world > 1 and not args.no_speed_aware and not args.direct and args.warmup >= 3:
+        run_step_device(st, actor, x, world)
+        lib.grpo_profile_enable(1)
+        lib.grpo_profile_read(None, None, 1)
+        for _ in range(args.warmup - 2):
+            run_step_device(st, actor, x, world)
+        torch.cuda.synchronize()
+        cal_ms = (ctypes.c_double * _lib.NUM_PHASES)()
+        lib.grpo_profile_read(cal_ms, None, 1)
+        lib.grpo_profile_enable(0)
+        mine = torch.tensor([sum(cal_ms) / (args.warmup - 2)], dtype=torch.float64, device=dev)
+        every = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine)
+        times = [float(t.item()) for t in every]
+        from spatialthinker_b200.sharding import speed_weighted_counts
+
+        counts = speed_weighted_counts(bsz, times, OPT_STEPS)
+        speed_aware = {"own_kernel_ms_per_step_on_equal_shards": [round(t, 1) for t in times], "sequences_per_rank": counts}
+        warm_done = args.warmup - 1
+        if any(c != counts[0] for c in counts):
+            actor.release_workspaces()
+            del actor, x
+            torch.cuda.empty_cache()
+            x = make_inputs(st, cfg, rank, world, dev, ragged, args.legacy_inputs, args.balance, counts, times)
+            tokens_local, tokens_total = count_tokens(x)
+            actor = build_actor(x)
     if args.direct:
         micro = args.micro_seqs or max(1, MAX_TOKENS // tlen)
         plan, counts = direct_plan(x, micro)
@@ -469,7 +528,7 @@ def main():
     else:
         seen = {}
         dev_step = lambda: seen.update(m=run_step_device(st, actor, x, world))  # noqa: E731
-    for _ in range(args.warmup):
+    for _ in range(args.warmup - warm_done):
         dev_step()
     actor.time_collectives = world > 1
     actor.collective_events = []
@@ -503,9 +562,8 @@ def main():
 
     # ---- the reference's shipped micro-batch size (4 sequences) with the deferred dW GEMM, a few steps
     records = []
-    if not args.no_records and not args.direct and not args.micro_seqs and (x["local"] // OPT_STEPS) % 4 == 0:
-        actor4 = st.DataParallelPPOActor(actor_config(st, x["local"], 4, want_entropy, args.entropy_coeff), x["weight"],
-                                         defer_dw=True)
+    if not args.no_records and not args.direct and not args.micro_seqs and (x["nominal_local"] // OPT_STEPS) % 4 == 0:
+        actor4 = build_actor(x, micro_seqs=4, defer=True)
         step4 = lambda: run_step_device(st, actor4, x, world)  # noqa: E731
         step4()
         k = max(2, args.steps // 10)
@@ -543,7 +601,7 @@ def main():
             kernels.append({"name": name, "launches": int(ph_cnt[i]), "avg_ms": ph_ms[i] / ph_cnt[i], "total_ms": ph_ms[i]})
     gemms = [k for k in kernels if k["name"].endswith("_gemm")]
     dom = max(gemms, key=lambda k: k["total_ms"])
-    rows_per_launch = tokens_local * args.steps / dom["launches"]  # every GEMM launch covers one chunk of (valid) rows
+    rows_per_launch = tokens_local * args.steps / dom["launches"]  # every GEMM launch covers one chunk of (valid) rows (rank 0's)
     achieved = 2.0 * hdim * vocab * rows_per_launch / (dom["avg_ms"] * 1e-3) / 1e12
     peak = peaks["sustained"]  # kernels are timed inside a seconds-long step under the power cap
     traffic = None
@@ -575,7 +633,7 @@ def main():
                    "parallelism": f"dp{world} by sequence" + ((", token-balanced rank shards (Karmarkar-Karp" + (", per optimizer step" if args.balance > 1 else "") + ")") if ragged and args.balance else "") + ", dW mean all-reduce (NCCL)",
                    "tokens_per_rank": x["tokens_per_rank"], "tokens_per_rank_unbalanced": x["tokens_per_rank_unbalanced"],
                    "mini_batch_token_spread_across_ranks": x["mini_batch_token_spread"],
-                   "records": records, "by_rank": by_rank},
+                   "speed_aware_shards": speed_aware, "records": records, "by_rank": by_rank},
         "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline, "e2e": e2e,
     }
     if not args.no_cpu:

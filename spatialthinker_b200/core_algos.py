@@ -13,7 +13,7 @@ The rest of the reference file rides on the same elementwise / warp-per-sequence
 from __future__ import annotations
 
 from abc import ABC, abstractmethod
-from typing import Sequence, Tuple
+from typing import Optional, Sequence, Tuple
 
 import numpy as np
 import torch
@@ -92,12 +92,14 @@ def compute_grpo_outcome_advantage_sharded(
     row_begin: int,
     eps: float = 1e-6,
     group=None,
+    rank_sizes: Optional[Sequence[int]] = None,
 ) -> Tuple[torch.Tensor, torch.Tensor]:
     """The same advantages when the batch is sharded by sequence over data-parallel ranks.
 
     ``token_level_rewards`` / ``response_mask`` are this rank's rows ``[row_begin, row_begin + bs_local)`` of the global
-    batch (equal row counts per rank, rank order = row order); ``index_all`` is the uid of EVERY sequence. Scores are
-    all-gathered (``bs_all`` floats over NCCL), the group statistics run redundantly on every rank.
+    batch (rank order = row order; equal row counts per rank unless ``rank_sizes`` lists them - speed-aware shards);
+    ``index_all`` is the uid of EVERY sequence. Scores are all-gathered (``bs_all`` floats over NCCL), the group
+    statistics run redundantly on every rank.
     """
     from .sharding import all_gather_rows
 
@@ -111,7 +113,7 @@ def compute_grpo_outcome_advantage_sharded(
     with torch.cuda.device(dev):
         _lib.check(lib.grpo_sequence_scores(rewards.data_ptr(), bsz, t_len, scores.data_ptr(), _lib.stream_ptr(dev)),
                    "grpo_sequence_scores")
-    scores_all = all_gather_rows(scores, group)
+    scores_all = all_gather_rows(scores, group, rank_sizes)
     bsz_all = scores_all.shape[0]
     if bsz_all != len(index_all):
         raise ValueError(f"index_all has {len(index_all)} entries but the gathered batch has {bsz_all} sequences")

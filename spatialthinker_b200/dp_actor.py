@@ -69,6 +69,10 @@ class ActorConfig:
     # loss is weighted by len(micro) / len(mini) - upstream's convention - instead of 1 / GA.
     use_dynamic_bsz: bool = False
     max_token_len_per_micro_batch: int = 37888  # two 18 944-row chunks of the GEMM pipeline
+    # extension (speed-aware shards, sharding.speed_weighted_counts): when the ranks hold DIFFERENT numbers of sequences per
+    # mini-batch, every rank scales its micro-batch losses for the same nominal mini-batch size (global batch / world size)
+    # so that the mean all-reduce over ranks still weights every sequence alike. 0: global_batch_size_per_device.
+    loss_scale_batch_size: int = 0
     # extension (config C4 of BASELINE.json): also compute the true per-token entropy lse - sum p z in the same pass and
     # log its masked mean as actor/entropy (the reference only logs the estimator -masked_mean(log p), dp_actor.py:253)
     log_true_entropy: bool = False
@@ -386,16 +390,20 @@ class DataParallelPPOActor:
         divisor ``len(mini) / len(micro)``."""
         cfg = self.config
         n = len(rows)
+        nominal = cfg.loss_scale_batch_size or n
         count = (lambda idx: None) if lens is None else (lambda idx: sum(lens[i] for i in idx))
         if cfg.use_dynamic_bsz:
             tokens = [lens[i] for i in rows] if lens is not None else [t_len] * n
             parts = rearrange_micro_batches(tokens, max(cfg.max_token_len_per_micro_batch, t_len), self.process_group,
                                             device=self.weight.device, num_micro_batches=num_micro)
-            return [([rows[i] for i in p], n / len(p), count([rows[i] for i in p])) for p in parts]
+            return [([rows[i] for i in p], nominal / len(p), count([rows[i] for i in p])) for p in parts]
         micro = cfg.micro_batch_size_per_device_for_update
-        assert n % micro == 0, f"only support equal chunk. Got size of DataProto {n} and chunk {n // max(micro, 1)}."
-        grad_accum = cfg.global_batch_size_per_device // micro
-        return [(rows[m0:m0 + micro], float(grad_accum), count(rows[m0:m0 + micro])) for m0 in range(0, n, micro)]
+        # the reference's split() only knows equal chunks (protocol.py:488-523); a speed-aware shard (loss_scale_batch_size
+        # set) may end in a shorter micro-batch, weighted by its own length like every other
+        assert n % micro == 0 or cfg.loss_scale_batch_size > 0, (
+            f"only support equal chunk. Got size of DataProto {n} and chunk {n // max(micro, 1)}.")
+        chunks = [rows[m0:m0 + micro] for m0 in range(0, n, micro)]
+        return [(c, nominal / len(c), count(c)) for c in chunks]  # full chunks: nominal / micro = the reference's GA (:233)
 
     def update_policy(self, data) -> Dict[str, Any]:
         """dp_actor.py:212-292: returns the reference's metrics dict (lists per micro-batch / per optimizer step).

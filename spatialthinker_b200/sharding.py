@@ -141,6 +141,80 @@ def balanced_rank_order(seqlens: Sequence[int], world_size: int, mini_batches: i
 
 
 # ----------------------------------------------------------------------------------------------------------------
+# speed-aware sharding: chips under a power cap do not run at the same clock
+# ----------------------------------------------------------------------------------------------------------------
+def speed_weighted_counts(total: int, step_times: Sequence[float], multiple: int = 1, max_shift: float = 0.10) -> List[int]:
+    """Sequences per rank proportional to each rank's measured speed (``1 / step_times[r]`` for EQUAL work), each a
+    multiple of ``multiple``, summing to ``total``.
+
+    Eight B200s of one box at the 1000 W cap differ by 4-7 % in sustained GEMM throughput (profiles/README.md, round 2), and
+    every optimizer step ends in an all-reduce: with equal shards the fast chips idle for that difference. The reference
+    assumes homogeneous GPUs (equal shards, ray_trainer.py:526-541). No rank's share moves by more than ``max_shift``."""
+    world = len(step_times)
+    assert total % multiple == 0 and total // multiple >= world
+    speeds = [1.0 / max(float(t), 1e-9) for t in step_times]
+    mean = sum(speeds) / world
+    speeds = [min(max(v, mean * (1.0 - max_shift)), mean * (1.0 + max_shift)) for v in speeds]
+    units = total // multiple
+    ideal = [units * v / sum(speeds) for v in speeds]
+    counts = [max(1, int(x)) for x in ideal]
+    # largest remainders get the units still to hand out (or give back)
+    order = sorted(range(world), key=lambda r: ideal[r] - counts[r], reverse=True)
+    i = 0
+    while sum(counts) < units:
+        counts[order[i % world]] += 1
+        i += 1
+    while sum(counts) > units:
+        r = max(range(world), key=lambda q: counts[q] - ideal[q])
+        counts[r] -= 1
+    return [c * multiple for c in counts]
+
+
+def weighted_balanced_cells(seqlens: Sequence[int], cell_sizes: Sequence[int], cell_weights: Sequence[float],
+                            refine_iters: int = 400) -> List[List[int]]:
+    """Assign every sequence to one of ``len(cell_sizes)`` cells with EXACTLY ``cell_sizes[c]`` sequences each and token
+    sums proportional to ``cell_weights`` (a cell = one rank's mini-batch; weight = that rank's speed).
+
+    Longest-processing-time greedy under capacity, then pairwise swaps between the most over- and under-filled cells.
+    With equal sizes and weights use :func:`balanced_rank_order` (the reference's Karmarkar-Karp) instead."""
+    import numpy as np
+
+    lens = np.asarray([int(x) for x in seqlens], dtype=np.int64)
+    sizes = [int(c) for c in cell_sizes]
+    assert sum(sizes) == len(lens) and all(c > 0 for c in sizes)
+    w = np.asarray(cell_weights, dtype=np.float64)
+    target = lens.sum() * w / w.sum()
+    cells: List[List[int]] = [[] for _ in sizes]
+    sums = np.zeros(len(sizes))
+    free = np.asarray(sizes, dtype=np.int64)
+    for i in np.argsort(-lens, kind="stable"):
+        # the cell that is furthest below its target PER FREE SLOT keeps long and short sequences mixed
+        score = np.where(free > 0, (target - sums) / np.maximum(free, 1), -np.inf)
+        c = int(np.argmax(score))
+        cells[c].append(int(i))
+        sums[c] += lens[i]
+        free[c] -= 1
+    for _ in range(refine_iters):
+        dev = sums - target
+        a, b = int(np.argmax(dev)), int(np.argmin(dev))
+        if a == b or dev[a] - dev[b] < 2:
+            break
+        ia, ib = np.asarray(cells[a]), np.asarray(cells[b])
+        want = (dev[a] - dev[b]) / 2.0  # moving `want` tokens from a to b equalises the two deviations
+        diff = lens[ia][:, None] - lens[ib][None, :]
+        gain = np.abs(diff - want)
+        k = int(np.argmin(gain))
+        x, y = divmod(k, len(ib))
+        d = int(diff[x, y])
+        if d <= 0 or d >= dev[a] - dev[b]:
+            break  # no swap brings the pair closer
+        cells[a][x], cells[b][y] = int(ib[y]), int(ia[x])
+        sums[a] -= d
+        sums[b] += d
+    return [sorted(c) for c in cells]
+
+
+# ----------------------------------------------------------------------------------------------------------------
 # collectives
 # ----------------------------------------------------------------------------------------------------------------
 def _world(group=None) -> int:
@@ -160,11 +234,21 @@ def allreduce_mean_(grad: torch.Tensor, group: Optional[dist.ProcessGroup] = Non
     return grad
 
 
-def all_gather_rows(local: torch.Tensor, group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
-    """Concatenate equally-sized per-rank row blocks (sequence scores, uid codes) in rank order."""
+def all_gather_rows(local: torch.Tensor, group: Optional[dist.ProcessGroup] = None,
+                    sizes: Optional[Sequence[int]] = None) -> torch.Tensor:
+    """Concatenate per-rank row blocks (sequence scores, uid codes) in rank order. ``sizes`` (rows per rank, known to
+    every rank) allows unequal blocks (speed-aware shards): blocks are padded to the largest for the collective."""
     ws = _world(group)
     if ws == 1:
         return local
-    out = [torch.empty_like(local) for _ in range(ws)]
-    dist.all_gather(out, local.contiguous(), group=group)
-    return torch.cat(out, dim=0)
+    if sizes is None:
+        out = [torch.empty_like(local) for _ in range(ws)]
+        dist.all_gather(out, local.contiguous(), group=group)
+        return torch.cat(out, dim=0)
+    assert len(sizes) == ws and local.shape[0] == sizes[dist.get_rank(group)]
+    cap = max(sizes)
+    padded = local.new_zeros((cap,) + tuple(local.shape[1:]))
+    padded[:local.shape[0]] = local
+    out = [torch.empty_like(padded) for _ in range(ws)]
+    dist.all_gather(out, padded, group=group)
+    return torch.cat([o[:n] for o, n in zip(out, sizes)], dim=0)

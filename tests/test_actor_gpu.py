@@ -338,3 +338,38 @@ def test_update_policy_streams_from_pinned_host(st, dev, dynamic):
     for a, b in zip(d0, d1):
         assert torch.equal(a, b)
     assert torch.equal(h0, h1)
+
+
+# ================================================================================================ speed-aware shards
+@pytest.mark.parametrize("dynamic", [False, True])
+def test_uneven_rank_shards_keep_the_gradient(st, dev, dynamic):
+    """ActorConfig.loss_scale_batch_size: two ranks holding 10 and 6 sequences of a 16-sequence mini-batch (speed-aware
+    shards) scale their losses for the nominal 8 - the mean of their dW over ranks is the gradient of the equal 8 + 8 split
+    and of the oracle's global loss. Dense masks: every token then weighs the same whichever rank and micro-batch holds it."""
+    bsz, tl, h, v = 16, 32, 128, 2048
+    x = _inputs(bsz, tl, h, v, 4, 0.1, seed=61, ragged=False)
+    w = x["weight"].to(dev)
+
+    def rank_dw(rows, mini, nominal):
+        cfg = st.ActorConfig(global_batch_size_per_device=mini, loss_scale_batch_size=nominal,
+                             micro_batch_size_per_device_for_update=2, use_dynamic_bsz=dynamic,
+                             max_token_len_per_micro_batch=3 * tl, use_kl_loss=True, kl_penalty="low_var_kl", kl_coef=0.01)
+        actor = st.DataParallelPPOActor(cfg, w)
+        grabbed = []
+        orig = actor._optimizer_step
+        actor._optimizer_step = lambda: (grabbed.append(actor.dweight.clone()), orig())[1]
+        sl = slice(*rows)
+        data = st.TensorBatch({"hidden_states": x["hidden"][sl].to(dev), "responses": x["labels"][sl].to(dev),
+                               "response_mask": x["mask"][sl].to(dev), "old_log_probs": x["old"][sl].to(dev),
+                               "advantages": x["adv"][sl].to(dev), "ref_log_probs": x["ref"][sl].to(dev)},
+                              meta_info={"temperature": 1.0})
+        actor.update_policy(data)
+        assert len(grabbed) == 1
+        return grabbed[0]
+
+    equal = 0.5 * (rank_dw((0, 8), 8, 0) + rank_dw((8, 16), 8, 0))
+    uneven = 0.5 * (rank_dw((0, 10), 10, 8) + rank_dw((10, 16), 6, 8))
+    assert rel(uneven, equal) < 2e-3
+    want = O.fused_loss_reference(x["hidden"], x["weight"], x["labels"], x["old"], x["adv"], x["mask"], x["ref"],
+                                  kl_penalty="low_var_kl", kl_coef=0.01, grad_accum=1.0, **CLIP)
+    assert rel(uneven, want["dweight"]) < TOL_REL and rel(equal, want["dweight"]) < TOL_REL

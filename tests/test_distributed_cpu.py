@@ -43,6 +43,12 @@ def _worker(rank, world, port, out):
         my_lens = [40, 30, 20, 10, 25, 35] if rank == 0 else [5, 5, 5, 5, 5, 5]
         parts = rearrange_micro_batches(my_lens, 60)
         assert len(parts) == 3 and sorted(i for p in parts for i in p) == list(range(6))
+        # (2c) unequal row blocks (speed-aware shards): sizes known to every rank, padded for the collective
+        sizes = [3, 5]
+        block = torch.arange(sizes[rank] * 2, dtype=torch.float32).view(sizes[rank], 2) + 100 * rank
+        got = all_gather_rows(block, sizes=sizes)
+        want_rows = torch.cat([torch.arange(n * 2, dtype=torch.float32).view(n, 2) + 100 * r for r, n in enumerate(sizes)])
+        assert torch.equal(got, want_rows)
         dw = res["dweight"].clone()
         allreduce_mean_(dw)  # (3) FSDP-style mean over ranks
         if rank == 0:

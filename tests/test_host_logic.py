@@ -345,3 +345,47 @@ def test_balanced_rank_order_balances_every_optimizer_step():
     assert (max(ranks) - min(ranks)) / max(ranks) < 1e-3
     with pytest.raises(AssertionError):
         balanced_rank_order(lens[:100], 8, 4)
+
+
+def test_speed_weighted_counts_and_weighted_cells():
+    """Speed-aware shards: sequence counts proportional to measured speed (multiples of the optimizer steps, bounded shift,
+    exact total) and, for ragged batches, cells with fixed sizes whose token sums follow the speeds."""
+    import random
+
+    from spatialthinker_b200.sharding import speed_weighted_counts, weighted_balanced_cells
+
+    times = [1232.1, 1221.7, 1293.4, 1240.4, 1213.2, 1269.2, 1231.1, 1256.2]  # measured on one 8 x B200 box, equal shards
+    counts = speed_weighted_counts(4096, times, 4)
+    assert sum(counts) == 4096 and all(c % 4 == 0 for c in counts)
+    pred = [c * t for c, t in zip(counts, times)]
+    assert (max(pred) - min(pred)) / max(pred) < 0.012 < (max(times) - min(times)) / max(times)  # 6.2 % -> within one 4-sequence step
+    assert speed_weighted_counts(4096, [1.0] * 8, 4) == [512] * 8
+    wild = speed_weighted_counts(4096, [1.0, 1.0, 1.0, 5.0], 4, max_shift=0.10)  # a straggler cannot push anyone past +-10 %
+    assert sum(wild) == 4096 and min(wild) >= 0.85 * 1024 and max(wild) <= 1.15 * 1024
+    rng = random.Random(3)
+    lens = [rng.randint(1, 4096) for _ in range(2048)]
+    sizes = [c // 4 for c in speed_weighted_counts(2048, times, 4) for _ in range(4)]
+    weights = [1.0 / t for t in times for _ in range(4)]
+    cells = weighted_balanced_cells(lens, sizes, weights)
+    assert [len(c) for c in cells] == sizes and sorted(i for c in cells for i in c) == list(range(2048))
+    cost = [sum(lens[i] for i in c) / w for c, w in zip(cells, weights)]  # tokens x time per token
+    assert (max(cost) - min(cost)) / max(cost) < 2e-3
+
+
+def test_bench_global_layout_speed_aware():
+    """bench.global_layout: equal shards reproduce the reference's balanced dispatch; given counts and step times, rank
+    offsets follow the counts and every optimizer step's predicted time is level across the ranks."""
+    import bench
+
+    cfg = ("h", "v", 1024, 512, 8, "test")
+    cfg = (64, 128) + cfg[2:]
+    lens, uid, per_rank, naive, spread, counts, offsets = bench.global_layout(cfg, 4, True, 2)
+    assert counts == [256] * 4 and offsets == [0, 256, 512, 768] and spread < 1e-3
+    assert sorted(uid.tolist()) == sorted(list(range(128)) * 8)
+    times = [100.0, 104.0, 97.0, 101.0]
+    lens2, uid2, per2, _, spread2, counts2, offsets2 = bench.global_layout(cfg, 4, True, 2, [252, 244, 268, 260], times)
+    assert counts2 == [252, 244, 268, 260] and offsets2 == [0, 252, 496, 764] and spread2 < 2e-3
+    assert sorted(lens2.tolist()) == sorted(lens.tolist()) and sorted(uid2.tolist()) == sorted(uid.tolist())
+    # dense: nothing to balance but the counts
+    _, _, per3, _, spread3, _, _ = bench.global_layout(cfg, 4, False, 2, [252, 244, 268, 260], times)
+    assert per3 == [c * 512 for c in [252, 244, 268, 260]]

@@ -18,7 +18,7 @@ cfg = tuple(cfg)
 dev = torch.device("cuda:0")
 torch.cuda.set_device(dev)
 x = bench.make_inputs(st, cfg, 0, 1, dev, False, False, 2)
-actor = st.DataParallelPPOActor(bench.actor_config(st, x["local"], 0, False, 0.0), x["weight"])
+actor = st.DataParallelPPOActor(bench.actor_config(st, x, 0, False, 0.0), x["weight"])
 for _ in range(2):
     bench.run_step_device(st, actor, x, 1)
 torch.cuda.synchronize()
