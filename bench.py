@@ -118,7 +118,7 @@ def global_layout(cfg, world, ragged, balance, counts=None, step_times=None):
     verl/trainer/ray_trainer.py:526-541 -> seqlen_balancing.py:150-181) when the batch is ragged, and additionally per
     optimizer step (balance == 2). ``counts`` / ``step_times`` (speed-aware shards): rank r gets counts[r] sequences and,
     for a ragged batch, tokens in proportion to its measured speed in every mini-batch."""
-    from spatialthinker_b200.sharding import balanced_rank_order, weighted_balanced_cells
+    from spatialthinker_b200.sharding import balanced_rank_order, speed_weights, weighted_balanced_cells
 
     _, _, bsz, tlen, n, _ = cfg
     gp = torch.Generator().manual_seed(7)
@@ -128,25 +128,25 @@ def global_layout(cfg, world, ragged, balance, counts=None, step_times=None):
     else:
         lens = torch.full((bsz,), tlen, dtype=torch.long)
     local = bsz // world
-    equal = counts is None or all(c == local for c in counts)
     counts = [local] * world if counts is None else list(counts)
     offsets = [sum(counts[:r]) for r in range(world)]
     naive = [int(lens[r * local:(r + 1) * local].sum()) for r in range(world)]
     if ragged and balance and world > 1:
-        if equal:
+        if step_times is None:
             # balance == 1: the reference's one partition of the whole batch; balance == 2 (default): every optimizer step's
             # mini-batch balanced across the ranks as well (sharding.balanced_rank_order)
             order = torch.tensor(balanced_rank_order(lens.tolist(), world, OPT_STEPS if balance > 1 else 1))
-        else:
+        else:  # speed-aware: every (rank, mini-batch) cell keeps its sequence count and gets tokens in proportion to speed
             sizes = [c // OPT_STEPS for c in counts for _ in range(OPT_STEPS)]
-            weights = [1.0 / step_times[r] for r in range(world) for _ in range(OPT_STEPS)]
+            sw = speed_weights(step_times)
+            weights = [sw[r] for r in range(world) for _ in range(OPT_STEPS)]
             cells = weighted_balanced_cells(lens.tolist(), sizes, weights)
             order = torch.tensor([i for cell in cells for i in cell])
         lens, uid = lens[order], uid[order]
     per_rank = [int(lens[offsets[r]:offsets[r] + counts[r]].sum()) for r in range(world)]
-    # worst relative imbalance of PREDICTED time at an optimizer step (tokens x the rank's time per token)
-    tpt = [1.0] * world if step_times is None else [step_times[r] for r in range(world)]
-    cells = [[float(lens[offsets[r] + m * (counts[r] // OPT_STEPS):offsets[r] + (m + 1) * (counts[r] // OPT_STEPS)].sum()) * tpt[r]
+    # worst relative deviation, at an optimizer step, of a rank's tokens from its share (equal, or its speed weight)
+    share = [1.0] * world if step_times is None else speed_weights(step_times)
+    cells = [[float(lens[offsets[r] + m * (counts[r] // OPT_STEPS):offsets[r] + (m + 1) * (counts[r] // OPT_STEPS)].sum()) / share[r]
               for r in range(world)] for m in range(OPT_STEPS)] if all(c >= OPT_STEPS for c in counts) else [[1.0]]
     spread = max((max(c) - min(c)) / max(max(c), 1e-9) for c in cells)
     return lens, uid.numpy(), per_rank, naive, spread, counts, offsets
@@ -510,10 +510,14 @@ def main():
         times = [float(t.item()) for t in every]
         from spatialthinker_b200.sharding import speed_weighted_counts
 
-        counts = speed_weighted_counts(bsz, times, OPT_STEPS)
-        speed_aware = {"own_kernel_ms_per_step_on_equal_shards": [round(t, 1) for t in times], "sequences_per_rank": counts}
+        # dense responses: the only way to move work is to move sequences; ragged ones: every rank keeps its sequence count
+        # (the reference's equal-size dispatch) and the faster ranks get the longer sequences
+        counts = [bsz // world] * world if ragged else speed_weighted_counts(bsz, times, OPT_STEPS)
+        speed_aware = {"own_kernel_ms_per_step_on_equal_shards": [round(t, 1) for t in times], "sequences_per_rank": counts,
+                       "how": "tokens per rank and mini-batch in proportion to speed, equal sequence counts" if ragged
+                              else "sequences per rank in proportion to speed"}
         warm_done = args.warmup - 1
-        if any(c != counts[0] for c in counts):
+        if ragged or any(c != counts[0] for c in counts):
             actor.release_workspaces()
             del actor, x
             torch.cuda.empty_cache()

@@ -394,8 +394,20 @@ class DataParallelPPOActor:
         count = (lambda idx: None) if lens is None else (lambda idx: sum(lens[i] for i in idx))
         if cfg.use_dynamic_bsz:
             tokens = [lens[i] for i in rows] if lens is not None else [t_len] * n
-            parts = rearrange_micro_batches(tokens, max(cfg.max_token_len_per_micro_batch, t_len), self.process_group,
-                                            device=self.weight.device, num_micro_batches=num_micro)
+            cap = max(cfg.max_token_len_per_micro_batch, t_len)
+            if min(tokens) == max(tokens):
+                # equal lengths (dense responses): every split into equal counts is perfectly balanced, so consecutive runs
+                # do - no partitioning work on the host and no row gather on the device (views of the batch)
+                num = num_micro if num_micro is not None else micro_batch_counts([sum(tokens)], cap, self.process_group,
+                                                                                 self.weight.device)[0]
+                base, extra = divmod(n, num)
+                edges = [0]
+                for j in range(num):
+                    edges.append(edges[-1] + base + (1 if j < extra else 0))
+                parts = [list(range(edges[j], edges[j + 1])) for j in range(num)]
+            else:
+                parts = rearrange_micro_batches(tokens, cap, self.process_group, device=self.weight.device,
+                                                num_micro_batches=num_micro)
             return [([rows[i] for i in p], nominal / len(p), count([rows[i] for i in p])) for p in parts]
         micro = cfg.micro_batch_size_per_device_for_update
         # the reference's split() only knows equal chunks (protocol.py:488-523); a speed-aware shard (loss_scale_batch_size

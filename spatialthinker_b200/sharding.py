@@ -143,18 +143,30 @@ def balanced_rank_order(seqlens: Sequence[int], world_size: int, mini_batches: i
 # ----------------------------------------------------------------------------------------------------------------
 # speed-aware sharding: chips under a power cap do not run at the same clock
 # ----------------------------------------------------------------------------------------------------------------
-def speed_weighted_counts(total: int, step_times: Sequence[float], multiple: int = 1, max_shift: float = 0.10) -> List[int]:
-    """Sequences per rank proportional to each rank's measured speed (``1 / step_times[r]`` for EQUAL work), each a
-    multiple of ``multiple``, summing to ``total``.
+SPEED_DAMPING = 0.75
+
+
+def speed_weights(step_times: Sequence[float], damping: float = SPEED_DAMPING, max_shift: float = 0.10) -> List[float]:
+    """Relative share of the work each rank should get, from its measured time per step on EQUAL work.
+
+    ``(mean_time / time) ** damping``, clipped to ``1 +- max_shift``. The damping is empirical: a chip that used to wait
+    at the all-reduce 5 % of the time and is then kept busy loses ~0.3 % of speed per percent of idle time it gives up
+    (power cap / temperature; profiles/README.md, round 2), so handing it the full ``1 / time`` share overshoots."""
+    times = [max(float(t), 1e-9) for t in step_times]
+    mean = sum(times) / len(times)
+    return [min(max((mean / t) ** damping, 1.0 - max_shift), 1.0 + max_shift) for t in times]
+
+
+def speed_weighted_counts(total: int, step_times: Sequence[float], multiple: int = 1, max_shift: float = 0.10,
+                          damping: float = SPEED_DAMPING) -> List[int]:
+    """Sequences per rank in proportion to :func:`speed_weights`, each a multiple of ``multiple``, summing to ``total``.
 
     Eight B200s of one box at the 1000 W cap differ by 4-7 % in sustained GEMM throughput (profiles/README.md, round 2), and
     every optimizer step ends in an all-reduce: with equal shards the fast chips idle for that difference. The reference
     assumes homogeneous GPUs (equal shards, ray_trainer.py:526-541). No rank's share moves by more than ``max_shift``."""
     world = len(step_times)
     assert total % multiple == 0 and total // multiple >= world
-    speeds = [1.0 / max(float(t), 1e-9) for t in step_times]
-    mean = sum(speeds) / world
-    speeds = [min(max(v, mean * (1.0 - max_shift)), mean * (1.0 + max_shift)) for v in speeds]
+    speeds = speed_weights(step_times, damping, max_shift)
     units = total // multiple
     ideal = [units * v / sum(speeds) for v in speeds]
     counts = [max(1, int(x)) for x in ideal]
