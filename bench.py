@@ -418,6 +418,9 @@ def main():
     ap.add_argument("--no-records", action="store_true", help="skip the extra record at 4-sequence micro-batches")
     ap.add_argument("--no-speed-aware", action="store_true",
                     help="N > 1: keep equal sequence counts per rank (default: re-deal sequences by measured per-rank speed)")
+    ap.add_argument("--peer", default="auto", choices=["auto", "on", "off"],
+                    help="N > 1: dW exchange over peer-mapped memory (this library's kernels over NVLink; auto = on when the "
+                         "GPUs can map each other's memory) or NCCL's fp32 all-reduce (off)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -485,7 +488,7 @@ def main():
 
     def build_actor(xx, micro_seqs=args.micro_seqs, defer=not args.no_defer_dw):
         return st.DataParallelPPOActor(actor_config(st, xx, micro_seqs, want_entropy, args.entropy_coeff), xx["weight"],
-                                       defer_dw=defer)
+                                       defer_dw=defer, peer_exchange={"auto": None, "on": True, "off": False}[args.peer])
 
     actor = build_actor(x)
     # ---- speed-aware shards (N > 1): the chips of one box differ by several percent in sustained throughput under the
@@ -563,6 +566,13 @@ def main():
     by_rank = {"allreduce_ms_per_step": [round(float(g[0]), 2) for g in gathered],
                "kernel_phase_ms_per_step": [round(float(g[1]), 1) for g in gathered]}
     n_micro = None if args.direct else len(seen["m"]["actor/pg_loss"])
+    if world == 1:
+        dw_exchange = "none (one GPU)"
+    elif not args.direct and actor._peer:
+        dw_exchange = ("peer-mapped memory, own kernels over NVLink: fp32 reduce-scatter + norm, clip + bf16 all-gather + zero "
+                       "(spatialthinker_b200/peer.py)")
+    else:
+        dw_exchange = "NCCL fp32 all-reduce (AVG), then norm + zero"
 
     # ---- the reference's shipped micro-batch size (4 sequences) with the deferred dW GEMM, a few steps
     records = []
@@ -634,7 +644,8 @@ def main():
                    "inputs": "round-1 (-3 + 0.1 randn)" if args.legacy_inputs else "SURVEY 8(d): old/ref = logp + 0.1 randn, 1% +-1.5 outliers",
                    "loss": "GRPO clip .2/.3/3.0 + low_var_kl 1e-2" + (f" - {args.entropy_coeff} * entropy" if args.entropy_coeff else ""),
                    "l2": "inputs (>= 30 GB) far exceed the 126 MB L2",
-                   "parallelism": f"dp{world} by sequence" + ((", token-balanced rank shards (Karmarkar-Karp" + (", per optimizer step" if args.balance > 1 else "") + ")") if ragged and args.balance else "") + ", dW mean all-reduce (NCCL)",
+                   "parallelism": f"dp{world} by sequence" + ((", token-balanced rank shards (Karmarkar-Karp" + (", per optimizer step" if args.balance > 1 else "") + ")") if ragged and args.balance else "") + ", dW averaged over ranks once per optimizer step",
+                   "dw_exchange": dw_exchange,
                    "tokens_per_rank": x["tokens_per_rank"], "tokens_per_rank_unbalanced": x["tokens_per_rank_unbalanced"],
                    "mini_batch_token_spread_across_ranks": x["mini_batch_token_spread"],
                    "speed_aware_shards": speed_aware, "records": records, "by_rank": by_rank},

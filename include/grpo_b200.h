@@ -167,6 +167,44 @@ int grpo_grad_scale_cast(float* grad, int64_t n, const float* scale_dev, float s
                          int zero_after, grpo_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * Gradient exchange of the fp32 dW accumulator over the GPUs of one NVSwitch box through PEER-MAPPED memory (replaces the
+ * fp32 gradient averaging FSDP performs for the reference, actor/config.py:58 + fsdp_workers.py:242-280, for the replicated
+ * lm_head weight, and the passes of _optimizer_step that follow it, dp_actor.py:155-167). One process per GPU; every
+ * process maps every rank's buffers (CUDA IPC) and passes the `world` pointers in rank order. All calls are
+ * stream-ordered; the caller brackets every data pass with grpo_peer_barrier on the same stream, on every rank:
+ *     barrier -> reduce_scatter_sumsq -> barrier -> [norm, clip coefficient] -> scale_cast_allgather -> barrier
+ *   grpo_peer_barrier  : flag_ptrs[q] = rank q's uint32[world] flag array (zero-initialised, peer-mapped). Announces
+ *                        `epoch` (increasing by one per call, never 0) to every rank and waits for theirs. A peer that
+ *                        does not arrive within timeout_ms (<= 0: 30 s) traps the kernel.
+ *   grpo_peer_reduce_scatter_sumsq : buf_ptrs[q] = rank q's copy of the fp32 [n] buffer (n % 8 == 0, 16-byte aligned).
+ *                        Slab `rank` (units of 8 elements, ceil(n / 8 / world) units per rank) of all copies is summed in
+ *                        rank order, scaled by 1/world and stored into THIS rank's copy; the slab's sum of squares goes
+ *                        to partial_ptrs[q][rank] (double[world] per rank, peer-mapped) for every q. scratch:
+ *                        GRPO_GRAD_SCRATCH_DOUBLES doubles of local device memory, ZERO before the first call.
+ *   grpo_peer_scale_cast_allgather : out_ptrs[q][slab] = bf16(grad[slab] * scale) for every q (out: bf16 [n] per rank,
+ *                        peer-mapped; scale = scale_dev[0] when given, else scale_host); zero_after: the whole local
+ *                        grad buffer is zeroed in the same pass.
+ *   grpo_peer_allreduce_mean : general in-place mean all-reduce of a peer-mapped fp32 [n] buffer (n % 4 == 0): this rank
+ *                        reduces its slab and writes the result into all copies. Barrier before and after.
+ *   Results are bit-identical on all ranks and from run to run (every element is summed by one rank, in rank order).
+ *   grpo_ipc_export / grpo_ipc_open / grpo_ipc_close: host-side CUDA IPC plumbing for those mappings. export describes a
+ *     device pointer as (64-byte handle of the allocation it lies in, byte offset); another PROCESS opens it on its own
+ *     current device (peer access is enabled on the way; a handle is mapped once per process and reference-counted) and
+ *     gets the mapped pointer; close drops the reference.
+ * ------------------------------------------------------------------------------------------------------------------ */
+#define GRPO_MAX_PEERS 8
+int grpo_ipc_export(const void* ptr, void* handle_out_64, int64_t* offset_out);
+int grpo_ipc_open(const void* handle_64, int64_t offset, void** ptr_out);
+int grpo_ipc_close(void* ptr, int64_t offset);
+int grpo_peer_barrier(void* const* flag_ptrs, int rank, int world, unsigned int epoch, int timeout_ms,
+                      grpo_stream_t stream);
+int grpo_peer_reduce_scatter_sumsq(void* const* buf_ptrs, void* const* partial_ptrs, int rank, int world, int64_t n,
+                                   double* scratch, grpo_stream_t stream);
+int grpo_peer_scale_cast_allgather(float* grad, void* const* out_ptrs, int rank, int world, int64_t n,
+                                   const float* scale_dev, float scale_host, int zero_after, grpo_stream_t stream);
+int grpo_peer_allreduce_mean(void* const* buf_ptrs, int rank, int world, int64_t n, grpo_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Token-level policy loss on given log-probs (no lm_head): the four masked means of compute_policy_loss
  * (core_algos.py:291-353), optionally the KL term (compute_kl :394-436) and dL/dlogp with
  * L = (pg + kl_coef * kl) / grad_accum.   acc_scratch: 16 doubles of device scratch.

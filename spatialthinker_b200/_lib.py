@@ -55,6 +55,13 @@ _SIGNATURES = {
     "grpo_deferred_dw_flush": (c_int, [c_int64, c_int64, c_int64, c_int64, _P, _P, c_size_t, _P]),
     "grpo_grad_sumsq": (c_int, [_P, c_int64, c_int, c_int, _P, _P, _P]),
     "grpo_grad_scale_cast": (c_int, [_P, c_int64, _P, c_float, _P, c_int, _P]),
+    "grpo_ipc_export": (c_int, [_P, _P, _P]),
+    "grpo_ipc_open": (c_int, [_P, c_int64, _P]),
+    "grpo_ipc_close": (c_int, [_P, c_int64]),
+    "grpo_peer_barrier": (c_int, [_P, c_int, c_int, ctypes.c_uint, c_int, _P]),
+    "grpo_peer_reduce_scatter_sumsq": (c_int, [_P, _P, c_int, c_int, c_int64, _P, _P]),
+    "grpo_peer_scale_cast_allgather": (c_int, [_P, _P, c_int, c_int, c_int64, _P, c_float, c_int, _P]),
+    "grpo_peer_allreduce_mean": (c_int, [_P, c_int, c_int, c_int64, _P]),
     "grpo_policy_loss_fwd_bwd": (
         c_int,
         [_P, _P, _P, _P, _P, c_int, c_int64, c_float, c_float, c_float, c_int, c_float, c_float, _P, _P, _P, _P],

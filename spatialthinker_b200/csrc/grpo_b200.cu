@@ -19,6 +19,7 @@
 #include "lmhead_kernels.cuh"
 #include "logits_kernels.cuh"
 #include "loss_kernels.cuh"
+#include "peer_kernels.cuh"
 
 namespace grpo {
 
@@ -1023,6 +1024,183 @@ int grpo_grad_scale_cast(float* grad, int64_t n, const float* scale_dev, float s
   if (n == 0) return 0;
   grad_scale_cast_kernel<<<kGradBlocks * 2, kGradThreads, 0, stream>>>(grad, static_cast<size_t>(n), scale_dev, scale_host,
                                                                        static_cast<__nv_bfloat16*>(out_bf16), zero_after);
+  count_launch();
+  GRPO_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// CUDA IPC plumbing for the peer-mapped buffers: the exporter describes a device pointer as (handle of the allocation it
+// lies in, byte offset), the importer maps that allocation into ITS OWN device's address space (peer access is enabled on
+// the way) and gets the pointer back. Host-side only, called once per buffer at set-up. Two exported pointers may lie in
+// one allocation (a caching allocator carves tensors out of larger segments): a handle is opened once per process and
+// reference-counted here.
+namespace {
+struct IpcMapping {
+  char handle[64];
+  void* base;
+  int refs;
+};
+std::mutex g_ipc_mutex;
+std::vector<IpcMapping> g_ipc_open;
+}  // namespace
+
+int grpo_ipc_export(const void* ptr, void* handle_out_64, int64_t* offset_out) {
+  if (!ptr || !handle_out_64 || !offset_out) return fail(GRPO_ERR_ARG, "null argument");
+  using RangeFn = CUresult (*)(CUdeviceptr*, size_t*, CUdeviceptr);
+  static RangeFn range_fn = nullptr;
+  if (!range_fn) {
+    void* fp = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fp, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return fail(GRPO_ERR_DRIVER, "cuMemGetAddressRange entry point not available");
+    range_fn = reinterpret_cast<RangeFn>(fp);
+  }
+  CUdeviceptr base = 0;
+  size_t size = 0;
+  const CUresult r = range_fn(&base, &size, reinterpret_cast<CUdeviceptr>(ptr));
+  if (r != CUDA_SUCCESS) return fail(GRPO_ERR_DRIVER, "cuMemGetAddressRange failed with CUresult %d", (int)r);
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  GRPO_CUDA(cudaIpcGetMemHandle(&h, reinterpret_cast<void*>(base)));
+  memcpy(handle_out_64, &h, 64);
+  *offset_out = static_cast<int64_t>(reinterpret_cast<CUdeviceptr>(ptr) - base);
+  return 0;
+}
+int grpo_ipc_open(const void* handle_64, int64_t offset, void** ptr_out) {
+  if (!handle_64 || !ptr_out || offset < 0) return fail(GRPO_ERR_ARG, "bad argument");
+  std::lock_guard<std::mutex> lock(g_ipc_mutex);
+  for (IpcMapping& m : g_ipc_open) {
+    if (!memcmp(m.handle, handle_64, 64)) {
+      ++m.refs;
+      *ptr_out = static_cast<uint8_t*>(m.base) + offset;
+      return 0;
+    }
+  }
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle_64, 64);
+  void* base = nullptr;
+  GRPO_CUDA(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+  IpcMapping m;
+  memcpy(m.handle, handle_64, 64);
+  m.base = base;
+  m.refs = 1;
+  g_ipc_open.push_back(m);
+  *ptr_out = static_cast<uint8_t*>(base) + offset;
+  return 0;
+}
+int grpo_ipc_close(void* ptr, int64_t offset) {
+  if (!ptr) return 0;
+  void* base = static_cast<uint8_t*>(ptr) - offset;
+  std::lock_guard<std::mutex> lock(g_ipc_mutex);
+  for (size_t i = 0; i < g_ipc_open.size(); ++i) {
+    if (g_ipc_open[i].base != base) continue;
+    if (--g_ipc_open[i].refs == 0) {
+      g_ipc_open.erase(g_ipc_open.begin() + static_cast<long>(i));
+      GRPO_CUDA(cudaIpcCloseMemHandle(base));
+    }
+    return 0;
+  }
+  return fail(GRPO_ERR_ARG, "pointer was not opened with grpo_ipc_open");
+}
+
+namespace {
+// the rank-ordered pointer table of one peer-mapped buffer
+int peer_table(void* const* ptrs, int rank, int world, unsigned align_mask, const char* what, PeerPtrs* out) {
+  if (!ptrs || world < 1 || world > kMaxPeers || rank < 0 || rank >= world)
+    return fail(GRPO_ERR_ARG, "%s: need 1..%d ranks and a valid rank", what, kMaxPeers);
+  *out = PeerPtrs{};
+  for (int q = 0; q < world; ++q) {
+    if (!ptrs[q] || (reinterpret_cast<uintptr_t>(ptrs[q]) & align_mask))
+      return fail(GRPO_ERR_ARG, "%s: pointer of rank %d is null or misaligned", what, q);
+    out->p[q] = ptrs[q];
+  }
+  return 0;
+}
+// slab of `rank`: items [rank * per, min((rank + 1) * per, items)), per = ceil(items / world)
+inline void peer_slab(size_t items, int rank, int world, size_t* i0, size_t* i1) {
+  const size_t per = (items + static_cast<size_t>(world) - 1) / static_cast<size_t>(world);
+  *i0 = per * static_cast<size_t>(rank) < items ? per * static_cast<size_t>(rank) : items;
+  *i1 = *i0 + per < items ? *i0 + per : items;
+}
+}  // namespace
+
+#define GRPO_PEER_DISPATCH(world, LAUNCH) \
+  switch (world) {                        \
+    case 1: LAUNCH(1); break;             \
+    case 2: LAUNCH(2); break;             \
+    case 3: LAUNCH(3); break;             \
+    case 4: LAUNCH(4); break;             \
+    case 5: LAUNCH(5); break;             \
+    case 6: LAUNCH(6); break;             \
+    case 7: LAUNCH(7); break;             \
+    default: LAUNCH(8); break;            \
+  }
+
+int grpo_peer_barrier(void* const* flag_ptrs, int rank, int world, unsigned int epoch, int timeout_ms,
+                      grpo_stream_t stream) {
+  PeerPtrs f;
+  if (int rc = peer_table(flag_ptrs, rank, world, 3u, "peer barrier", &f)) return rc;
+  const uint64_t timeout_ns = static_cast<uint64_t>(timeout_ms > 0 ? timeout_ms : 30000) * 1000000ull;
+  peer_barrier_kernel<<<1, 32, 0, stream>>>(f, rank, world, epoch, timeout_ns);
+  count_launch();
+  GRPO_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int grpo_peer_allreduce_mean(void* const* buf_ptrs, int rank, int world, int64_t n, grpo_stream_t stream) {
+  PeerPtrs b;
+  if (int rc = peer_table(buf_ptrs, rank, world, 15u, "peer all-reduce", &b)) return rc;
+  if (n < 0 || n % 4 != 0) return fail(GRPO_ERR_ARG, "element count must be a non-negative multiple of 4");
+  if (n == 0 || world == 1) return 0;
+  size_t v0, v1;
+  peer_slab(static_cast<size_t>(n) / 4, rank, world, &v0, &v1);
+  if (v0 >= v1) return 0;
+  const float inv = 1.f / static_cast<float>(world);
+#define GRPO_PEER_AR(W) peer_allreduce_mean_kernel<W><<<kPeerBlocks, kPeerThreads, 0, stream>>>(b, v0, v1, inv)
+  GRPO_PEER_DISPATCH(world, GRPO_PEER_AR)
+#undef GRPO_PEER_AR
+  count_launch();
+  GRPO_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int grpo_peer_reduce_scatter_sumsq(void* const* buf_ptrs, void* const* partial_ptrs, int rank, int world, int64_t n,
+                                   double* scratch, grpo_stream_t stream) {
+  PeerPtrs b, parts;
+  if (int rc = peer_table(buf_ptrs, rank, world, 15u, "peer reduce-scatter", &b)) return rc;
+  if (int rc = peer_table(partial_ptrs, rank, world, 7u, "peer reduce-scatter partials", &parts)) return rc;
+  if (!scratch) return fail(GRPO_ERR_ARG, "scratch must not be null");
+  if (n < 0 || n % 8 != 0) return fail(GRPO_ERR_ARG, "element count must be a non-negative multiple of 8");
+  size_t u0, u1;
+  peer_slab(static_cast<size_t>(n) / 8, rank, world, &u0, &u1);
+  const float inv = 1.f / static_cast<float>(world);
+#define GRPO_PEER_RS(W)                                                                                             \
+  peer_reduce_scatter_sumsq_kernel<W><<<kPeerBlocks, kPeerThreads, 0, stream>>>(                                    \
+      b, static_cast<float4*>(b.p[rank]), rank, 2 * u0, 2 * u1, inv, parts, scratch)
+  GRPO_PEER_DISPATCH(world, GRPO_PEER_RS)
+#undef GRPO_PEER_RS
+  count_launch();
+  GRPO_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int grpo_peer_scale_cast_allgather(float* grad, void* const* out_ptrs, int rank, int world, int64_t n,
+                                   const float* scale_dev, float scale_host, int zero_after, grpo_stream_t stream) {
+  PeerPtrs outs;
+  if (int rc = peer_table(out_ptrs, rank, world, 15u, "peer all-gather", &outs)) return rc;
+  if (!grad || (reinterpret_cast<uintptr_t>(grad) & 15u)) return fail(GRPO_ERR_ARG, "grad is null or not 16-byte aligned");
+  if (n < 0 || n % 8 != 0) return fail(GRPO_ERR_ARG, "element count must be a non-negative multiple of 8");
+  if (n == 0) return 0;
+  const size_t units = static_cast<size_t>(n) / 8;
+  size_t u0, u1;
+  peer_slab(units, rank, world, &u0, &u1);
+#define GRPO_PEER_AG(W)                                                                                           \
+  peer_scale_cast_allgather_kernel<W><<<kPeerBlocks, kPeerThreads, 0, stream>>>(grad, units, u0, u1, scale_dev, \
+                                                                                scale_host, outs, zero_after)
+  GRPO_PEER_DISPATCH(world, GRPO_PEER_AG)
+#undef GRPO_PEER_AG
+#undef GRPO_PEER_DISPATCH
   count_launch();
   GRPO_CUDA(cudaGetLastError());
   return 0;

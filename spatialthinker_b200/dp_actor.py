@@ -210,6 +210,7 @@ class DataParallelPPOActor:
         compact_padding: bool = True,
         defer_dw: bool = True,
         reduce_body_grads: Optional[bool] = None,
+        peer_exchange: Optional[bool] = None,
     ):
         self.config = config
         self.rank = int(os.getenv("RANK", "0"))
@@ -226,6 +227,12 @@ class DataParallelPPOActor:
         # Costs one more chunk workspace (6 GB at the 7B head), allocated when the first small micro-batch arrives.
         self.defer_dw = defer_dw
         self.reduce_body_grads = reduce_body_grads
+        # dW exchange over peer-mapped memory (peer.PeerGroup: reduce-scatter + norm, then clip + bf16 all-gather + zero, this
+        # library's kernels over NVLink) instead of NCCL's fp32 all-reduce followed by separate norm / clip / cast passes.
+        # None: on when the ranks of the group share one host (GRPO_PEER_EXCHANGE=0 turns it off); if the GPUs cannot map
+        # each other's memory every rank falls back to NCCL together, with a warning. True: failure to set it up raises.
+        self.peer_exchange = peer_exchange
+        self._peer = None          # None: not tried yet, False: unavailable, else (PeerGroup, dW buffer, gradient buffer)
         self._deferred: Optional[DeferredDW] = None
         self.dweight: Optional[torch.Tensor] = None  # fp32 [V, H] accumulator ("main grad") across micro-batches
         self._grad_buf: Optional[torch.Tensor] = None  # bf16 [V, H]: what the optimizer sees as weight.grad
@@ -245,6 +252,11 @@ class DataParallelPPOActor:
         if self._deferred is not None:
             self._deferred.release()
         self._deferred = None
+        if self._peer:  # collective: the other ranks have these buffers mapped
+            group, dw_buf, grad_buf = self._peer
+            group.release(dw_buf)
+            group.release(grad_buf)
+        self._peer = None
         self.dweight = None
         self._grad_buf = None
         self._stager = None
@@ -278,11 +290,86 @@ class DataParallelPPOActor:
                     out.append(p)
         return out
 
+    def _setup_peer(self) -> None:
+        """Map the fp32 accumulator and the bf16 gradient buffer into every rank of the group (collective, once)."""
+        if self._peer is not None:
+            return
+        self._peer = False
+        world = dist.get_world_size(self.process_group) if dist.is_available() and dist.is_initialized() else 1
+        want = self.peer_exchange
+        if want is None:
+            want = os.environ.get("GRPO_PEER_EXCHANGE", "1") != "0"
+        if world == 1 or not want or not self.weight.is_cuda or self.dweight.numel() % 8 != 0:
+            return
+        from . import peer
+
+        try:
+            group = peer.get_group(self.process_group, self.weight.device)
+            if self._grad_buf is None or self._grad_buf.shape != self.weight.shape:
+                self._grad_buf = torch.empty(self.weight.shape, dtype=torch.bfloat16, device=self.weight.device)
+            self._peer = (group, group.register(self.dweight), group.register(self._grad_buf))
+        except peer.PeerUnavailable as exc:
+            if self.peer_exchange:
+                raise
+            if self.rank == 0:
+                warnings.warn(f"DataParallelPPOActor: peer-mapped dW exchange unavailable ({exc}); using NCCL's all-reduce.")
+
+    def _timed(self, fn):
+        """Run ``fn`` between CUDA events when the bench asks for per-rank collective times."""
+        if not self.time_collectives:
+            return fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = fn()
+        e1.record()
+        self.collective_events.append((e0, e1))
+        return out
+
+    def _optimizer_step_peer(self) -> torch.Tensor:
+        """``_optimizer_step`` over peer-mapped memory: the same arithmetic - fp32 mean over ranks, global norm, clip,
+        bf16 gradient for the optimizer, non-finite skip - with the exchange and the passes over ``dW`` fused
+        (csrc/peer_kernels.cuh). Every rank issues the same kernels whatever the norm turns out to be."""
+        group, dw_buf, grad_buf = self._peer
+        cfg = self.config
+        opt = self.actor_optimizer
+        others = self._other_params()
+        reduce_body = bool(self.reduce_body_grads)
+        wgrad = self.weight.grad if (opt is not None and self.weight.is_leaf) else None
+        if wgrad is not None and wgrad is not self._grad_buf:
+            # a tied embedding's share of this parameter's gradient joins the accumulator BEFORE the exchange: it is
+            # averaged with it (already-averaged values are a fixed point of the mean)
+            self.dweight.add_(wgrad)
+        if reduce_body:
+            for p in others:
+                allreduce_mean_(p.grad, self.process_group)
+        total = self._timed(lambda: group.reduce_scatter_sumsq(dw_buf))
+        if others:
+            norms = torch._foreach_norm([p.grad for p in others])
+            total = total + torch.stack([n.double() for n in norms]).square().sum()
+        grad_norm = total.sqrt().float().squeeze(0)
+        clip = torch.clamp(cfg.max_grad_norm / (grad_norm + 1e-6), max=1.0).reshape(1)
+        self._timed(lambda: group.scale_cast_allgather(dw_buf, grad_buf, clip, zero_after=True))
+        if opt is None:  # head-only accumulation (bench, tests): the clipped bf16 gradient stays in self._grad_buf
+            return grad_norm
+        if not bool(torch.isfinite(grad_norm)):
+            print("Gradient norm is not finite. Skip update.")
+        else:
+            self.weight.grad = self._grad_buf
+            for p in others:
+                p.grad.mul_(clip.reshape(()).to(p.grad.dtype))
+            opt.step()
+        opt.zero_grad()
+        if self.weight.is_leaf:
+            self.weight.grad = None
+        return grad_norm
+
     def _optimizer_step(self) -> torch.Tensor:
         """dp_actor.py:155-167. The head's ``dW`` is averaged over ranks in fp32 (FSDP's ``mp_reduce_dtype``,
         actor/config.py:58); the clip coefficient comes from the global norm over EVERY parameter the optimizer holds;
         a non-finite norm skips the update (the reference's host branch) and the gradients are dropped."""
         assert self.dweight is not None
+        if self._peer:
+            return self._optimizer_step_peer()
         cfg = self.config
         if self.time_collectives:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -453,6 +540,7 @@ class DataParallelPPOActor:
 
         if self.dweight is None:
             self.dweight = torch.zeros(self.weight.shape, dtype=torch.float32, device=self.weight.device)
+        self._setup_peer()
         defer = None
         if self.defer_dw and cfg.entropy_coeff == 0.0:
             if self._deferred is None or self._deferred.dweight is not self.dweight:
