@@ -66,7 +66,7 @@ def _expected(copies, max_norm):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("world", [1, 2, 3, 8])
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 8])
 @pytest.mark.parametrize("n", [8 * 5, 8 * 4099, 8 * 148 * 4 * 512 * 2 + 8 * 77])
 def test_peer_kernels_with_ranks_played_by_local_buffers(world, n):
     from spatialthinker_b200 import _lib

@@ -25,7 +25,7 @@ def main():
     ap.add_argument("--rows", type=int, default=151936)
     ap.add_argument("--hidden", type=int, default=3584)
     ap.add_argument("--iters", type=int, default=10)
-    ap.add_argument("--log", default="")
+    ap.add_argument("--save", default=os.environ.get("GRPO_PEER_LOG", ""), help="file for rank 0's lines")
     args = ap.parse_args()
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
@@ -145,8 +145,8 @@ def main():
     say(f"optimizer-step exchange: {t[0] / tp[0]:.2f}x faster than the NCCL path")
     group.release(gbuf)
     group.release(obuf)
-    if rank == 0 and args.log:
-        with open(args.log, "w") as f:
+    if rank == 0 and args.save:
+        with open(args.save, "w") as f:
             f.write("\n".join(lines) + "\n")
     dist.destroy_process_group()
     sys.exit(0 if float(flag) == 1.0 else 1)
