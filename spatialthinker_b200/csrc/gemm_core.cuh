@@ -70,6 +70,12 @@ struct TileSched {
                           // side work on the SAME K range of neighbouring tiles, so the operand panels those tiles share
                           // are fetched from HBM once, as in the whole-tile rounds
   uint32_t max_progress;  // most K-blocks any one group loads (progress-window bookkeeping)
+  // Serpentine K order: every other whole tile of a CTA group walks its K-blocks backwards. All groups are in the same
+  // round at the same time (and in lock-step within it), so the operand that EVERY round re-reads along K - the scaled
+  // hidden chunk in the dW GEMM (136 MB, just over the L2), W in the dHidden GEMM - is met again first where it was
+  // touched last: the tail of one round is still L2-resident at the head of the next (a cyclic walk evicts exactly what
+  // it needs next). Each tile still sums its K-blocks in a fixed order: results stay reproducible.
+  uint32_t serpentine;
 };
 
 // work unit u -> (tile, K-block range)
@@ -258,17 +264,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       const bool do_sync = leader && sched.sync_period != 0 && sched.sync_ctr != nullptr;
       uint32_t progress = 0, rounds_done = 0;
       bool give_up = false;
-      for (uint32_t u = first_tile; u < num_units; u += tile_step) {
+      uint32_t round = 0;
+      for (uint32_t u = first_tile; u < num_units; u += tile_step, ++round) {
         uint32_t t, kb0, kb1, m_blk, n_blk;
         decode_unit(sched, u, t, kb0, kb1);
         decode_tile(sched, t, m_blk, n_blk);
         const int32_t m0 = static_cast<int32_t>(m_blk * Cfg::kTileRows + rank * Cfg::kRowsPerCta);
         const int32_t n0 = static_cast<int32_t>(n_blk * BLOCK_N + rank * Cfg::kLoadN);
-        for (uint32_t kb = kb0; kb < kb1; ++kb, ++progress) {
+        const bool backwards = sched.serpentine != 0 && (round & 1u) != 0 && u < sched.whole_tiles;
+        for (uint32_t step = kb0; step < kb1; ++step, ++progress) {
+          const uint32_t kb = backwards ? kb0 + (kb1 - 1 - step) : step;  // the K-block this stage carries
           if (do_sync && progress != 0 && progress % sched.sync_period == 0)
             progress_sync(sched.sync_ctr, ++rounds_done, tile_step, give_up);
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          if (kb == kb0) GRPO_TR(10, (u - first_tile) / tile_step);
+          if (step == kb0) GRPO_TR(10, (u - first_tile) / tile_step);
           const int32_t k0 = static_cast<int32_t>(kb * kBlockK);
           uint8_t* sa = smem_a + stage * Cfg::kABytes;
           uint8_t* sb = smem_b + stage * Cfg::kBBytes;

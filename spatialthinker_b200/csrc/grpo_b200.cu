@@ -214,6 +214,8 @@ struct Knobs {
   // the same fp32 words in completion order) and the one-hot rows of dW summed in row order instead of with atomics
   // (grad_kernels.cuh). Costs ~1 % (profiles/); off by default.
   int deterministic = 0;
+  // serpentine K order (TileSched::serpentine), bit 0: dW GEMM, bit 1: dHidden GEMM
+  int k_serp = 0;
 };
 static Knobs g_knobs;
 static std::once_flag g_knobs_once;
@@ -242,6 +244,7 @@ static void init_knobs() {
     g_knobs.acc_lead = env_int("GRPO_ACC_LEAD", g_knobs.acc_lead);
     g_knobs.st_hint = env_int("GRPO_ST_HINT", g_knobs.st_hint) & 3;
     g_knobs.deterministic = env_int("GRPO_DETERMINISTIC", g_knobs.deterministic) != 0;
+    g_knobs.k_serp = env_int("GRPO_K_SERP", g_knobs.k_serp) & 3;
   });
 }
 
@@ -597,6 +600,7 @@ static int dw_gemm(const DevInfo& dev, const Workspace& w, const __nv_bfloat16* 
   s.sync_period = static_cast<uint32_t>(dev.sync_dw);
   s.sync_ctr = w.sync + 2;
   s.split_tail = static_cast<uint32_t>(dev.dw_split);  // the epilogue accumulates (reduce-add): K slices just add up
+  s.serpentine = static_cast<uint32_t>(dev.k_serp & 1);
   s.probe = dev.clk_probe ? w.probe + 2048 : nullptr;
   if (dev.l2_hints & 2) {  // the (scaled) hidden chunk is re-read for every vocab block; the stash streams through once
     s.hint_a = kEvictFirst;
@@ -689,6 +693,7 @@ static int chunk_backward(const DevInfo& dev, const Workspace& w, const __nv_bfl
     s.sync_period = static_cast<uint32_t>(dev.sync_dh);
     s.sync_ctr = w.sync + 1;
     s.probe = dev.clk_probe ? w.probe + 1024 : nullptr;
+    s.serpentine = static_cast<uint32_t>((dev.k_serp >> 1) & 1);
     if (dev.l2_hints & 16) s.hint_b = kEvictLast;  // W is re-read by every round of tiles; the stash streams through once
     GRPO_TRY((launch_gemm_any<A_BLOCKED_K, true, EpiBF16<1, kBlockN>, EpiBF16<2, kBlockN>>(
         dev, w.stash, n, w.stash_vb, weight, h, h, v, s, p1, p2, stream)));
@@ -755,6 +760,7 @@ int grpo_set_option(const char* name, int value) {
   else if (!strcmp(name, "epi_share")) g_knobs.epi_share = value != 0;
   else if (!strcmp(name, "dh_split")) g_knobs.dh_split = value != 0;
   else if (!strcmp(name, "deterministic")) g_knobs.deterministic = value != 0;
+  else if (!strcmp(name, "k_serp")) g_knobs.k_serp = value & 3;
   else if (!strcmp(name, "chunk_rows")) g_knobs.chunk_rows = value > 0 ? (value + 511) / 512 * 512 : 0;
   else return fail(GRPO_ERR_ARG, "unknown option '%s'", name);
   return 0;

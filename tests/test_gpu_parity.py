@@ -237,6 +237,44 @@ def test_dhidden_split_path_matches_direct(st, dev, rows, h, v, dent):
         assert rel(outs[0][0][keep.to(dev)], hf.grad[keep]) < TOL_REL
 
 
+@pytest.mark.parametrize("rows,h,v", [(1500, 2560, 8192 + 136), (4608, 2304, 4096)])
+def test_serpentine_k_order_matches_forward_order(st, dev, rows, h, v):
+    """Option k_serp: every other whole tile of a CTA pair walks its K-blocks backwards (dW GEMM: bit 0, dHidden GEMM:
+    bit 1) so that the operand every round re-reads is met again where it was touched last. Same sums in another order:
+    dW (fp32) agrees to fp32 rounding, dHidden (bf16 out) to one bf16 rounding. First shape: 17 x 10 dW tiles = 2.3 rounds
+    over the 74 CTA pairs (dHidden: one round, untouched); second: 9 x 9 dHidden tiles = 1.1 rounds on the direct bf16
+    path (dW: one round, untouched)."""
+    from spatialthinker_b200 import _lib
+
+    lib = _lib.load()
+    hid, w = O.synth_head(rows, h, v, seed=9, sigma_w=0.1)
+    g = torch.Generator().manual_seed(9)
+    lab = torch.randint(0, v, (rows,), generator=g)
+    gl = torch.randn(rows, generator=g) / rows
+    outs = []
+    try:
+        _lib.check(lib.grpo_set_option(b"dh_split", 0), "set_option")
+        for serp in (0, 3):
+            _lib.check(lib.grpo_set_option(b"k_serp", serp), "set_option")
+            hd, wd = hid.to(dev).requires_grad_(True), w.to(dev).requires_grad_(True)
+            lp, _ = st.fused_lm_head_log_probs(hd, wd, lab.to(dev), 1.0)
+            (lp * gl.to(dev)).sum().backward()
+            torch.cuda.synchronize()
+            outs.append((lp.detach().clone(), hd.grad.clone(), wd.grad.clone()))
+    finally:
+        lib.grpo_set_option(b"k_serp", 0)
+        lib.grpo_set_option(b"dh_split", DH_SPLIT_DEFAULT)
+    assert torch.equal(outs[0][0], outs[1][0])     # the logits GEMM is untouched
+    assert rel(outs[0][1], outs[1][1]) < 2e-3      # bf16 outputs of fp32 sums taken in another order
+    assert rel(outs[0][2], outs[1][2]) < 1e-5
+    pairs = 74
+    dw_rounds = -(-v // 512) * -(-h // 256) > pairs
+    dh_rounds = -(-rows // 512) * -(-h // 256) > pairs
+    if dw_rounds:  # (with one round dW may still differ in its last bits: the one-hot rows are fp32 atomics)
+        assert not torch.equal(outs[0][2], outs[1][2]), "the option did not reach the dW GEMM"
+    assert torch.equal(outs[0][1], outs[1][1]) != dh_rounds, "dHidden GEMM: the option acts exactly on tiles of later rounds"
+
+
 def test_epilogue_variants_agree(st, dev):
     """Softmax-epilogue variants (plain loop / pipelined TMEM drain / stash through bulk tensor stores) and dW-epilogue
     variants must give the same log-probs bit for bit and the same gradients up to fp32 accumulation order."""

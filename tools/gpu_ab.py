@@ -45,7 +45,7 @@ for spec in args.variants:  # the workspace must fit the largest chunk setting a
     lib.grpo_set_option(b"ksub", 2)
 ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
 DEFAULTS = {"cta_group": 2, "fwd_panel": 4864, "sync_fwd": 28, "sync_dh": 8, "sync_dw": 8, "l2_hints": 0, "dh_m_fast": 0, "chunk_rows": 0, "ksub": 2, "wait_hint_ns": 10000000,
-            "epi_mode": 7, "dw_tma": 1, "acc_lead": 2, "clk_probe": 1, "st_hint": 3, "dw_split": 1, "epi_share": 0, "dh_split": 0}
+            "epi_mode": 7, "dw_tma": 1, "acc_lead": 2, "clk_probe": 1, "st_hint": 3, "dw_split": 1, "epi_share": 0, "dh_split": 0, "k_serp": 0}
 
 
 def apply(spec):
