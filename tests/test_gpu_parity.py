@@ -241,7 +241,7 @@ def test_dhidden_split_path_matches_direct(st, dev, rows, h, v, dent):
 def test_serpentine_k_order_matches_forward_order(st, dev, rows, h, v):
     """Option k_serp: every other whole tile of a CTA pair walks its K-blocks backwards (dW GEMM: bit 0, dHidden GEMM:
     bit 1) so that the operand every round re-reads is met again where it was touched last. Same sums in another order:
-    dW (fp32) agrees to fp32 rounding, dHidden (bf16 out) to one bf16 rounding. First shape: 17 x 10 dW tiles = 2.3 rounds
+    dW and dHidden (both handed back as bf16) agree to one bf16 rounding. First shape: 17 x 10 dW tiles = 2.3 rounds
     over the 74 CTA pairs (dHidden: one round, untouched); second: 9 x 9 dHidden tiles = 1.1 rounds on the direct bf16
     path (dW: one round, untouched)."""
     from spatialthinker_b200 import _lib
@@ -266,13 +266,12 @@ def test_serpentine_k_order_matches_forward_order(st, dev, rows, h, v):
         lib.grpo_set_option(b"dh_split", DH_SPLIT_DEFAULT)
     assert torch.equal(outs[0][0], outs[1][0])     # the logits GEMM is untouched
     assert rel(outs[0][1], outs[1][1]) < 2e-3      # bf16 outputs of fp32 sums taken in another order
-    assert rel(outs[0][2], outs[1][2]) < 1e-5
+    assert rel(outs[0][2], outs[1][2]) < 2e-3      # autograd hands dW back in the parameter's dtype (bf16)
     pairs = 74
-    dw_rounds = -(-v // 512) * -(-h // 256) > pairs
-    dh_rounds = -(-rows // 512) * -(-h // 256) > pairs
-    if dw_rounds:  # (with one round dW may still differ in its last bits: the one-hot rows are fp32 atomics)
+    if -(-v // 512) * -(-h // 256) > pairs:        # more than one round of dW tiles: the order of some sums changed
         assert not torch.equal(outs[0][2], outs[1][2]), "the option did not reach the dW GEMM"
-    assert torch.equal(outs[0][1], outs[1][1]) != dh_rounds, "dHidden GEMM: the option acts exactly on tiles of later rounds"
+    if -(-rows // 512) * -(-h // 256) > pairs:
+        assert not torch.equal(outs[0][1], outs[1][1]), "the option did not reach the dHidden GEMM"
 
 
 def test_epilogue_variants_agree(st, dev):
