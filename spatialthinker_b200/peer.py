@@ -32,7 +32,7 @@ from . import _lib
 
 MAX_PEERS = 8
 _FLAGS_OFFSET, _PARTIALS_OFFSET, _CONTROL_BYTES = 0, 64, 4096
-DEFAULT_TIMEOUT_MS = 30000
+DEFAULT_TIMEOUT_MS = 120000  # a rank that is this late is gone (NCCL's own watchdog waits ten minutes)
 
 
 class PeerUnavailable(RuntimeError):
