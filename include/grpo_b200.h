@@ -203,6 +203,8 @@ int grpo_peer_reduce_scatter_sumsq(void* const* buf_ptrs, void* const* partial_p
 int grpo_peer_scale_cast_allgather(float* grad, void* const* out_ptrs, int rank, int world, int64_t n,
                                    const float* scale_dev, float scale_host, int zero_after, grpo_stream_t stream);
 int grpo_peer_allreduce_mean(void* const* buf_ptrs, int rank, int world, int64_t n, grpo_stream_t stream);
+/* host-only: element range [e0, e1) of the slab `rank` owns in the two fused passes above (n % 8 == 0) */
+int grpo_debug_peer_slab(int64_t n, int rank, int world, int64_t* e0, int64_t* e1);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Token-level policy loss on given log-probs (no lm_head): the four masked means of compute_policy_loss

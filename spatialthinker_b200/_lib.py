@@ -62,6 +62,7 @@ _SIGNATURES = {
     "grpo_peer_reduce_scatter_sumsq": (c_int, [_P, _P, c_int, c_int, c_int64, _P, _P]),
     "grpo_peer_scale_cast_allgather": (c_int, [_P, _P, c_int, c_int, c_int64, _P, c_float, c_int, _P]),
     "grpo_peer_allreduce_mean": (c_int, [_P, c_int, c_int, c_int64, _P]),
+    "grpo_debug_peer_slab": (c_int, [c_int64, c_int, c_int, _P, _P]),
     "grpo_policy_loss_fwd_bwd": (
         c_int,
         [_P, _P, _P, _P, _P, c_int, c_int64, c_float, c_float, c_float, c_int, c_float, c_float, _P, _P, _P, _P],

@@ -1131,6 +1131,18 @@ inline void peer_slab(size_t items, int rank, int world, size_t* i0, size_t* i1)
 }
 }  // namespace
 
+// element range [e0, e1) of the slab `rank` reduces in grpo_peer_reduce_scatter_sumsq / grpo_peer_scale_cast_allgather
+// (host-only; lets the host-side mirror peer.slab_bounds be checked against the partition the kernels are launched with)
+int grpo_debug_peer_slab(int64_t n, int rank, int world, int64_t* e0, int64_t* e1) {
+  if (!e0 || !e1 || n < 0 || n % 8 != 0 || world < 1 || world > kMaxPeers || rank < 0 || rank >= world)
+    return fail(GRPO_ERR_ARG, "peer slab: bad argument");
+  size_t u0, u1;
+  peer_slab(static_cast<size_t>(n) / 8, rank, world, &u0, &u1);
+  *e0 = static_cast<int64_t>(u0 * 8);
+  *e1 = static_cast<int64_t>(u1 * 8);
+  return 0;
+}
+
 #define GRPO_PEER_DISPATCH(world, LAUNCH) \
   switch (world) {                        \
     case 1: LAUNCH(1); break;             \

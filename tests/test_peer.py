@@ -29,6 +29,23 @@ def test_slab_partition_covers_every_element_once():
             assert max(e1 - e0 for e0, e1 in edges) <= 8 * (-(-(n // 8) // world))
 
 
+def test_host_mirror_of_the_slab_partition_matches_the_library():
+    """peer.slab_bounds (used by tests and tools to know which rank reduces what) against the partition the library
+    launches its kernels with (grpo_debug_peer_slab, host-only)."""
+    from spatialthinker_b200 import _lib
+    from spatialthinker_b200.peer import slab_bounds
+
+    lib = _lib.load()
+    e0, e1 = ctypes.c_int64(-1), ctypes.c_int64(-1)
+    for n in (0, 8, 8 * 7, 8 * 1001, 151936 * 3584, 152064 * 2048):
+        for world in range(1, 9):
+            for rank in range(world):
+                assert lib.grpo_debug_peer_slab(n, rank, world, ctypes.byref(e0), ctypes.byref(e1)) == 0
+                assert (e0.value, e1.value) == slab_bounds(n, rank, world), (n, rank, world)
+    assert lib.grpo_debug_peer_slab(12, 0, 2, ctypes.byref(e0), ctypes.byref(e1)) == -1
+    assert lib.grpo_debug_peer_slab(16, 2, 2, ctypes.byref(e0), ctypes.byref(e1)) == -1
+
+
 def test_peer_entry_points_reject_bad_arguments():
     """Argument checks come before any CUDA call: they answer GRPO_ERR_ARG on a box without a GPU too."""
     from spatialthinker_b200 import _lib
