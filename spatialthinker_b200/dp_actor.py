@@ -248,7 +248,9 @@ class DataParallelPPOActor:
 
     def release_workspaces(self) -> None:
         """Give back the deferred-dW chunk workspace, the fp32 accumulator and the gradient buffer (e.g. before the
-        rollout engine needs the memory); they are rebuilt on the next ``update_policy``."""
+        rollout engine needs the memory); they are rebuilt on the next ``update_policy``. With the peer exchange on this
+        is COLLECTIVE over the group: the other ranks have the accumulator and the gradient buffer mapped and must unmap
+        them before the memory may be freed."""
         if self._deferred is not None:
             self._deferred.release()
         self._deferred = None
