@@ -380,6 +380,28 @@ def update_policy_reference(
     return {"metrics": metrics, "steps": steps}
 
 
+def averaged_clipped_gradient(rank_grads: Sequence[torch.Tensor], max_grad_norm: float,
+                              other_sumsq: float = 0.0) -> Dict[str, torch.Tensor]:
+    """What every rank's optimizer sees for one replicated bf16 parameter after the reference's optimizer step
+    preamble: FSDP averages the ranks' gradients in fp32 (``mp_reduce_dtype``, verl/workers/actor/config.py:58;
+    verl/workers/fsdp_workers.py:242-280), ``clip_grad_norm_`` scales by ``min(1, max_norm / (norm + 1e-6))`` with the
+    norm over ALL parameters (verl/workers/actor/dp_actor.py:155-167; ``other_sumsq`` = the other parameters' share),
+    and the gradient handed to the optimizer has the parameter's dtype.
+
+    The fp32 sum runs in RANK ORDER and is multiplied by the fp32 reciprocal of the world size - the order the peer
+    exchange fixes (csrc/peer_kernels.cuh); any other order is an equally valid FSDP result, to fp32 rounding.
+    Returns mean (fp32), norm (fp64 scalar), clip (fp32 scalar), grad (bf16).
+    """
+    world = len(rank_grads)
+    mean = rank_grads[0].to(torch.float32).clone()
+    for g in rank_grads[1:]:
+        mean += g.to(torch.float32)
+    mean *= torch.tensor(1.0, dtype=torch.float32) / world
+    norm = (mean.double().square().sum() + other_sumsq).sqrt()
+    clip = torch.clamp(max_grad_norm / (norm.float() + 1e-6), max=1.0)
+    return {"mean": mean, "norm": norm, "clip": clip, "grad": (mean * clip).to(torch.bfloat16)}
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # synthetic inputs (SURVEY.md §8(d)) - shared by tests, smoke() and bench.py so every arm sees the same tensors
 # ----------------------------------------------------------------------------------------------------------------

@@ -71,15 +71,31 @@ def test_peer_entry_points_reject_bad_arguments():
 
 
 def _expected(copies, max_norm):
-    """fp32 mean in rank order, global norm in fp64, clip coefficient, bf16 gradient - with torch on the host."""
-    world = len(copies)
-    s = copies[0].clone()
-    for c in copies[1:]:
-        s += c
-    s *= torch.tensor(1.0, dtype=torch.float32) / world  # the kernel multiplies by the fp32 reciprocal 1.f / W
-    norm = s.double().square().sum().sqrt()
-    clip = torch.clamp(max_norm / (norm.float() + 1e-6), max=1.0)
-    return s, norm, clip, (s * clip).to(torch.bfloat16)
+    """fp32 mean in rank order, global norm in fp64, clip coefficient, bf16 gradient - the CPU oracle's restatement."""
+    from oracle import grpo_oracle as O
+
+    want = O.averaged_clipped_gradient(copies, max_norm)
+    return want["mean"], want["norm"], want["clip"], want["grad"]
+
+
+def test_oracle_of_the_exchange_is_torch_clip_grad_norm_on_the_fp32_mean():
+    """Pins oracle.averaged_clipped_gradient to the functions the reference itself calls (dp_actor.py:155-167):
+    ``clip_grad_norm_`` over several parameters holding the rank-averaged fp32 gradients."""
+    from oracle import grpo_oracle as O
+
+    gen = torch.Generator().manual_seed(3)
+    for world, max_norm in ((2, 0.5), (3, 1.0), (8, 1e6)):
+        grads = [torch.randn(4096, generator=gen) * (1 + q) for q in range(world)]
+        other = torch.randn(777, generator=gen)
+        head = torch.nn.Parameter(torch.zeros(4096))
+        body = torch.nn.Parameter(torch.zeros(777))
+        head.grad = torch.stack(grads).sum(0) / world
+        body.grad = other.clone()
+        total = torch.nn.utils.clip_grad_norm_([head, body], max_norm=max_norm)
+        got = O.averaged_clipped_gradient(grads, max_norm, other_sumsq=float(other.double().square().sum()))
+        assert abs(float(got["norm"]) - float(total)) <= 1e-5 * float(total)
+        assert torch.allclose(got["mean"] * got["clip"], head.grad, rtol=1e-5, atol=1e-8)
+        assert got["grad"].dtype == torch.bfloat16 and (float(got["clip"]) == 1.0) == (max_norm == 1e6)
 
 
 @pytest.mark.gpu
